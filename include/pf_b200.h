@@ -1,0 +1,141 @@
+/*
+ * pf_b200.h -- C ABI of the B200-native bg-forecast hot path (libpf_b200.so).
+ *
+ * The reference (nianticlabs/panoptic-forecasting) has no native layer: the path below is
+ * pure PyTorch + torch_scatter.  These entry points are what a binding on the reference
+ * side calls instead (INTEGRATION.md shows the ctypes stubs).  Conventions:
+ *   - every function returns 0 on success, a positive cudaError_t on a CUDA failure, or a
+ *     negative PF_E* code on a bad argument; pf_last_error() gives a message.
+ *   - `*_dev` pointers are device memory owned by the caller; the library never frees or
+ *     reallocates them.  Work space is caller-provided (query `*_workspace_bytes`).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work is
+ *     enqueued asynchronously on it; nothing synchronises unless stated.
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points fail.
+ */
+#ifndef PF_B200_H_
+#define PF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_EINVAL (-1)   /* bad argument (null pointer, non-positive size, unsupported shape) */
+#define PF_ENOMEM (-2)   /* work space too small */
+#define PF_ESTATE (-3)   /* handle not ready (weights missing) */
+
+int pf_version(void);
+const char* pf_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage A: unproject -> rigid chain -> reproject -> 4-way splat -> nearest-depth select.
+ * Replaces PCTransformModel.predict,
+ *   reference panoptic_forecasting/models/pc_transform/pc_transform_model.py:26-150
+ * including its torch_scatter.scatter_min call (:118-119) and the gather/index_put tail
+ * (:120-139).
+ *
+ *   depth_dev   f32 [b,t,H,W]    metric depth of each source pixel
+ *   mask_dev    u8  [b,t,H,W]    depth_mask (0/1)
+ *   seg_dev     u8  [b,t,H,W,payload]  payload = 1 (label) or 3 (is_img RGB)
+ *   K, Kinv     f32 [b,3,3]      intrinsics and torch.inverse(intrinsics)      (DEVICE memory)
+ *   E, Einv     f32 [b,4,4]      extrinsics and torch.inverse(extrinsics)      (DEVICE memory)
+ *   T           f32 [b,t,4,4]    target_T                                      (DEVICE memory)
+ *   lut_dev     u8  [256] or NULL  optional label remap applied at gather time (payload 1 only)
+ *   out_seg_dev u8  [b,H,W,payload]   0 where no valid point won the cell
+ *   out_depth_dev f32 [b,H,W]    winning z'; -1 for untouched cells; max(z')+1 for cells won by
+ *                                an invalid point (reference semantics, :105,:136-139)
+ *   out_coords_dev i64 [b,t,H,W,2] or NULL   clamped floor(u'),floor(v') (reference 'result2d', :147)
+ * All t frames of one batch item compete in ONE z-buffer (the reference's only_this_ind=None
+ * mode); the per-frame mode (only_this_ind=i) is the same call with t=1 on frame i's slices.
+ * Ties on depth go to the lowest flattened source index e = replica*t*N + frame*N + v*W + u.
+ * ------------------------------------------------------------------------------------- */
+size_t pf_zsplat_workspace_bytes(int b, int t, int H, int W);
+
+int pf_zsplat_forward(const float* depth_dev, const uint8_t* mask_dev, const uint8_t* seg_dev,
+                      const float* K_dev, const float* Kinv_dev,
+                      const float* E_dev, const float* Einv_dev, const float* T_dev,
+                      int b, int t, int H, int W, int payload,
+                      const uint8_t* lut_dev,
+                      uint8_t* out_seg_dev, float* out_depth_dev, int64_t* out_coords_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Same, with HOST buffers: copies inputs to the device, runs, copies seg/depth back and
+ * synchronises the stream.  This is the end-to-end call bench.py times as `e2e`. */
+int pf_zsplat_forward_host(const float* depth, const uint8_t* mask, const uint8_t* seg,
+                           const float* K, const float* Kinv, const float* E, const float* Einv,
+                           const float* T, int b, int t, int H, int W, int payload,
+                           const uint8_t* lut, uint8_t* out_seg, float* out_depth);
+
+/* ---------------------------------------------------------------------------------------
+ * Disk-hop emulation between stage A and stage B (fused on device):
+ *   exporter: u16 = round(clamp(d + 1, 0, 255) * 256)
+ *             reference experiments/export_cityscapes_segmentation_results.py:119-122
+ *   bg dataset: d = u16/256 - 1; mask = d > 0; d[~mask] = -1; d[mask] clamped to [min,max]
+ *             reference data/datasets/bg_dataset.py:223-230
+ * in/out f32 [n]; out_mask u8 [n].
+ * ------------------------------------------------------------------------------------- */
+int pf_depth_disk_hop(const float* depth_dev, float* out_depth_dev, uint8_t* out_mask_dev,
+                      size_t n, float min_depth, float max_depth, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage B: BGModel forward / predict on the HarDNet-70 segmentation net.
+ * Replaces reference panoptic_forecasting/models/bg/bg_model.py:53-71,91-102 and
+ * panoptic_forecasting/models/bg/hardnet.py:16-25,176-240,243-258,262-327,353-387.
+ * The topology (stem 16/24/32/48, growth 10/16/18/24/32, layers 4/4/8/8/8, 1x1 widths
+ * 64/96/160/224/320) is the reference's; conv index order below is the order in which the
+ * reference's forward executes them (base.0 .. base.3, block layers, 1x1, ..., decoder).
+ * ------------------------------------------------------------------------------------- */
+typedef struct pf_bgnet pf_bgnet_t;
+
+typedef struct {
+  int cin, cout, ksize, stride;
+  char name[64];      /* state_dict prefix, e.g. "model.base.4.layers.2" */
+} pf_conv_info_t;
+
+/* precision: 0 = fp32 SIMT kernels (bit-faithful to 1e-6),
+ *            1 = tensor-core (tcgen05) split-bf16 3-pass (fp32-faithful to ~3e-5). */
+int pf_bgnet_create(pf_bgnet_t** out, int num_classes, int num_inputs, int use_depth, int precision);
+void pf_bgnet_destroy(pf_bgnet_t* net);
+int pf_bgnet_num_convs(const pf_bgnet_t* net);          /* ConvLayers (conv+BN+ReLU), excludes finalConv */
+int pf_bgnet_conv_info(const pf_bgnet_t* net, int i, pf_conv_info_t* info);
+/* HOST pointers; weight is [cout,cin,k,k] fp32 as in the state_dict; BN folded here. */
+int pf_bgnet_load_conv(pf_bgnet_t* net, int i, const float* weight, const float* bn_weight,
+                       const float* bn_bias, const float* bn_mean, const float* bn_var, float eps);
+int pf_bgnet_load_final(pf_bgnet_t* net, const float* weight /*[classes,48]*/, const float* bias);
+int pf_bgnet_set_depth_norm(pf_bgnet_t* net, float mean, float std);
+
+size_t pf_bgnet_workspace_bytes(const pf_bgnet_t* net, int b, int H, int W);
+
+/*   labels_dev  u8  [b,t,H,W]   class ids; ids >= num_classes contribute an all-zero one-hot
+ *   depth_dev   f32 [b,t,H,W]   mask_dev u8 [b,t,H,W]
+ *   out_seg_*   argmax of the bilinearly (align_corners) upsampled logits at final_h x final_w:
+ *               u8 [b,final_h,final_w] and/or i64 (either may be NULL)
+ *   out_quarter_dev f32 [b,classes,H/4,W/4] or NULL   ('orig_size_logits')
+ *   out_full_dev    f32 [b,classes,final_h,final_w] or NULL ('logits')
+ */
+int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* depth_dev,
+                     const uint8_t* mask_dev, int b, int H, int W, int final_h, int final_w,
+                     uint8_t* out_seg_u8_dev, int64_t* out_seg_i64_dev,
+                     float* out_quarter_dev, float* out_full_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* number of kernel launches one pf_bgnet_forward enqueues (for bench.py's gpu_launches) */
+int pf_bgnet_launches_per_forward(const pf_bgnet_t* net);
+int pf_zsplat_launches_per_forward(void);
+
+/* Layer-level debug/test hooks: run ONE ConvLayer i on an NCHW fp32 device tensor. */
+int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_dev, int b, int H, int W,
+                        float* y_nchw_dev, void* stream);
+
+/* Stand-alone fused bilinear(align_corners) upsample + argmax over NCHW fp32 logits
+ * (reference hardnet.py:373-377 + bg_model.py:98). */
+int pf_upsample_argmax(const float* logits_nchw_dev, int b, int classes, int h, int w,
+                       int final_h, int final_w, uint8_t* out_seg_u8_dev, int64_t* out_seg_i64_dev,
+                       float* out_full_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PF_B200_H_ */

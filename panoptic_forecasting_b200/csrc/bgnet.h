@@ -1,0 +1,74 @@
+// Internal (non-ABI) description of the HarDNet-70 execution plan shared by the kernel files.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "pf_common.cuh"
+
+namespace pf {
+
+constexpr int kMaxSegs = 10;     // conv1x1_up reads <=5 upsampled block-output slots + <=5 skip slots
+constexpr int kChanAlign = 8;    // every activation slot starts at, and is padded to, 8 channels
+
+struct SegRef {                  // a channel slice of an NHWC activation buffer
+  int buf = -1;
+  int coff = 0;                  // first channel (multiple of kChanAlign)
+  int c = 0;                     // true channel count
+  int cpad() const { return (c + kChanAlign - 1) / kChanAlign * kChanAlign; }
+};
+
+struct BufDesc {
+  int shift = 0;                 // spatial size = (H >> shift, W >> shift)
+  int cstride = 0;               // channels per pixel (sum of padded slots)
+  size_t offset_floats = 0;      // per-image offset inside the arena, filled at plan time
+};
+
+struct ConvDesc {
+  std::string name;
+  int cin = 0, cout = 0, ksize = 3, stride = 1;
+  bool relu = true;
+  std::vector<SegRef> in;        // in reference cat order
+  SegRef out;
+  int kpad = 0;                  // sum of padded input channels
+  int coutpad = 0;               // cout padded to 16
+  // device weights (fp32 path): w[tap][kpad][coutpad], bias[coutpad]
+  float* w_dev = nullptr;
+  float* bias_dev = nullptr;
+  bool loaded = false;
+  std::vector<float> w_host;     // folded, packed like w_dev (kept for re-packing by the tensor-core path)
+  std::vector<float> bias_host;
+};
+
+enum StepType { STEP_FIRST = 0, STEP_CONV = 1, STEP_POOL = 2, STEP_UPSAMPLE = 3, STEP_HEAD = 4 };
+
+struct Step {
+  StepType type;
+  int conv = -1;                 // STEP_FIRST / STEP_CONV / STEP_HEAD(final conv index)
+  std::vector<SegRef> in;        // STEP_POOL (1 seg) / STEP_UPSAMPLE (n segs)
+  SegRef out;
+};
+
+// Device-side views --------------------------------------------------------------------------
+struct SegView {
+  const float* base;             // pixel (0,0) of image 0, channel coff
+  int cstride;
+  int cpad;
+};
+
+struct ConvLaunch {
+  SegView segs[kMaxSegs];
+  int nseg;
+  int b, Hin, Win, Hout, Wout;
+  size_t in_img_stride[kMaxSegs];  // floats per image for each seg's buffer
+  float* out;                    // pixel (0,0) of image 0, channel out.coff
+  int out_cstride;
+  size_t out_img_stride;
+  const float* w;
+  const float* bias;
+  int kpad, coutpad, cout_store; // cout_store = channels written (cout padded to 8)
+  int relu;
+};
+
+int launch_conv_simt(const ConvLaunch& L, int ksize, int stride, cudaStream_t st);
+
+}  // namespace pf

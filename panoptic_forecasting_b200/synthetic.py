@@ -1,0 +1,172 @@
+"""Seeded synthetic inputs for the bg-forecast hot path (no dataset, no network).
+
+Shapes/dtypes follow what the reference datasets hand to the models:
+  PCTransformModel.predict inputs  (pc_transform_model.py:27-32)
+  BGModel.predict inputs           (bg_model.py:91-95, bg_dataset.py:223-261)
+Camera/ego formulas follow data/data_utils.py:74-78 (extrinsics = vehicle_T_camera @ flu_T_rdf),
+:117-165 (unicycle ego step, inverted) and :170-203 (yaw/pitch/roll rotation); they are
+re-derived here because the reference helpers use the removed ``np.float``.
+"""
+import numpy as np
+import torch
+
+CITYSCAPES_K = (2262.52, 2265.3017905988554, 1096.98, 513.137)  # fx, fy, u0, v0
+
+
+def intrinsics_mat(h=1024, w=2048):
+    fx, fy, u0, v0 = CITYSCAPES_K
+    sx, sy = w / 2048.0, h / 1024.0
+    K = np.eye(3)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = fx * sx, fy * sy, u0 * sx, v0 * sy
+    return K
+
+
+def extrinsics_mat(yaw=0.0, pitch=0.038, roll=0.0, t=(1.7, 0.1, 1.22)):
+    sy_, cy = np.sin(yaw), np.cos(yaw)
+    sp, cp = np.sin(pitch), np.cos(pitch)
+    sr, cr = np.sin(roll), np.cos(roll)
+    R = np.array([[cy * cp, cy * sp * sr - sy_ * cr, cy * sp * cr + sy_ * sr],
+                  [sy_ * cp, sy_ * sp * sr + cy * cr, sy_ * sp * cr - cy * sr],
+                  [-sp, cp * sr, cp * cr]])
+    V = np.eye(4)
+    V[:3, :3] = R
+    V[:3, 3] = t
+    flu_T_rdf = np.eye(4)
+    flu_T_rdf[:3, :3] = np.array([[0, 0, 1], [-1, 0, 0], [0, -1, 0]], dtype=np.float64)
+    return V @ flu_T_rdf
+
+
+def vehicle_now_T_prev(speed, yaw_rate, dt):
+    if abs(yaw_rate) < 0.000175:
+        x, y, th = dt * speed, 0.0, 0.0
+    else:
+        r = speed / yaw_rate
+        wt = yaw_rate * dt
+        x, y, th = r * np.sin(wt), r - r * np.cos(wt), wt
+    T = np.eye(4)
+    T[:3, :3] = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    T[:3, 3] = [x, y, 0]
+    return np.linalg.inv(T)
+
+
+def target_transforms(steps=(15, 12, 9), speed=10.0, yaw_rate=0.01, dt=1.0 / 17.0, rng=None):
+    """target_T[i]: source-frame-i vehicle coords -> target-frame vehicle coords
+    (pc_transform_dataset.py:165-186 accumulation)."""
+    out = []
+    for n in steps:
+        T = np.eye(4)
+        for k in range(n):
+            s = speed if rng is None else speed + rng.normal(0, 0.3)
+            yr = yaw_rate if rng is None else yaw_rate + rng.normal(0, 0.003)
+            T = vehicle_now_T_prev(s, yr, dt) @ T
+        out.append(T)
+    return np.stack(out)
+
+
+def _scene_realistic(rng, h, w, K, E):
+    """Ground plane + fronto-parallel boxes + far wall; labels piecewise constant."""
+    vs, us = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    fx, fy, u0, v0 = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    cam_h = 1.22
+    ry = (vs - v0) / fy
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ground = np.where(ry > 1e-3, cam_h / ry, np.inf)
+    depth = np.minimum(ground, 120.0)
+    seg = np.where(ground < 120.0, 0, 10).astype(np.uint8)  # road / sky-wall
+    seg[(ground < 120.0) & (np.abs((us - u0) / fx * depth) > 4.0)] = 1  # sidewalk
+    nbox = 20
+    for _ in range(nbox):
+        z = rng.uniform(6.0, 80.0)
+        bw, bh = rng.uniform(1.0, 8.0), rng.uniform(1.5, 10.0)
+        x0 = rng.uniform(-25.0, 25.0)
+        uL, uR = (x0 * fx / z + u0), ((x0 + bw) * fx / z + u0)
+        vB = cam_h * fy / z + v0
+        vT = (cam_h - bh) * fy / z + v0
+        m = (us >= uL) & (us < uR) & (vs >= vT) & (vs < vB) & (depth > z)
+        depth[m] = z
+        seg[m] = rng.integers(2, 19)
+    depth = depth * (1.0 + rng.normal(0, 2e-3, size=depth.shape))
+    return depth.astype(np.float32), seg
+
+
+def _blob_mask(rng, h, w, frac):
+    """~frac of pixels invalid, in rectangular blobs (moving-object masks)."""
+    mask = np.ones((h, w), dtype=bool)
+    target = frac * h * w
+    covered = 0
+    while covered < target:
+        bh = int(rng.integers(max(2, h // 32), max(3, h // 6)))
+        bw = int(rng.integers(max(2, w // 64), max(3, w // 8)))
+        y0 = int(rng.integers(0, h - bh + 1))
+        x0 = int(rng.integers(0, w - bw + 1))
+        covered += mask[y0:y0 + bh, x0:x0 + bw].sum()
+        mask[y0:y0 + bh, x0:x0 + bw] = False
+    return mask
+
+
+def make_pc_inputs(b=1, t=3, h=1024, w=2048, dist="R", seed=0, steps=(15, 12, 9), device="cpu"):
+    """Inputs dict for PCTransformModel.predict. dist: 'R' realistic, 'U' adversarial iid."""
+    rng = np.random.default_rng(seed)
+    K = intrinsics_mat(h, w)
+    E = extrinsics_mat()
+    depth = np.empty((b, t, h, w), np.float32)
+    seg = np.empty((b, t, h, w), np.uint8)
+    mask = np.empty((b, t, h, w), bool)
+    Ts = np.empty((b, t, 4, 4), np.float64)
+    for bi in range(b):
+        Ts[bi] = target_transforms(tuple(steps[i % len(steps)] for i in range(t)), rng=rng)
+        for ti in range(t):
+            if dist == "R":
+                depth[bi, ti], seg[bi, ti] = _scene_realistic(rng, h, w, K, E)
+                mask[bi, ti] = _blob_mask(rng, h, w, 0.15)
+            else:
+                depth[bi, ti] = rng.uniform(2.0, 82.0, size=(h, w)).astype(np.float32)
+                seg[bi, ti] = rng.integers(0, 19, size=(h, w), dtype=np.uint8)
+                mask[bi, ti] = rng.uniform(size=(h, w)) > 0.15
+    dev = torch.device(device)
+    return {
+        "intrinsics": torch.from_numpy(np.broadcast_to(K, (b, 3, 3)).copy()).float().to(dev),
+        "extrinsics": torch.from_numpy(np.broadcast_to(E, (b, 4, 4)).copy()).float().to(dev),
+        "depth": torch.from_numpy(depth).to(dev),
+        "depth_mask": torch.from_numpy(mask).to(dev),
+        "target_T": torch.from_numpy(Ts).float().to(dev),
+        "seg": torch.from_numpy(seg).to(dev),
+    }
+
+
+def make_bg_inputs(b=1, t=3, h=512, w=1024, seed=0, device="cpu", label_dtype=torch.int64):
+    """Inputs dict for BGModel.predict: labels iid {0..18},
+    depth U(0,100), mask = depth > 5."""
+    g = torch.Generator().manual_seed(seed)
+    seg = torch.randint(0, 19, (b, t, h, w), generator=g, dtype=torch.int64).to(label_dtype)
+    depth = torch.rand((b, t, h, w), generator=g) * 100.0
+    mask = depth > 5.0
+    dev = torch.device(device)
+    return {"seg": seg.to(dev), "depth": depth.to(dev), "depth_mask": mask.to(dev)}
+
+
+def make_bg_state_dict(ref_state_dict_like, seed=0):
+    """Seeded synthetic weights with randomised BatchNorm statistics (so folding is
+    exercised). ``ref_state_dict_like``: a state_dict giving names and shapes."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(ref_state_dict_like.keys()):      # sorted: independent of module registration order
+        v = ref_state_dict_like[k]
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros_like(v)
+        elif k in ("depth_mean",):
+            out[k] = torch.full_like(v, 30.0)
+        elif k in ("depth_std",):
+            out[k] = torch.full_like(v, 25.0)
+        elif k.endswith("norm.weight") or k.endswith("running_var"):
+            out[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith("norm.bias") or k.endswith("running_mean"):
+            out[k] = torch.randn(v.shape, generator=g) * 0.1
+        elif k.endswith("conv.weight") or k.endswith("finalConv.weight"):
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3]
+            out[k] = torch.randn(v.shape, generator=g) * (2.0 / fan_in) ** 0.5
+        elif k.endswith("finalConv.bias"):
+            out[k] = torch.randn(v.shape, generator=g) * 0.1
+        else:
+            raise KeyError(k)
+    return out
