@@ -61,6 +61,20 @@ int pf_zsplat_forward(const float* depth_dev, const uint8_t* mask_dev, const uin
                       uint8_t* out_seg_dev, float* out_depth_dev, int64_t* out_coords_dev,
                       void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Per-frame mode: the t frames do NOT compete; frame i is splatted into its own z-buffer, which
+ * is what the bg pipeline consumes (reference configs/bg/bg_val_mid.yaml:12-14 reads the
+ * `..._ind0_all/_ind1_all/_ind2_all` exports made with model.only_this_ind = 0,1,2).  One call
+ * == t reference predict() calls, including their per-call sentinel max(z')+1 (taken over the
+ * whole batch of that frame, pc_transform_model.py:105).  Same arguments as pf_zsplat_forward
+ * but out_seg_dev is u8 [b,t,H,W,payload] and out_depth_dev f32 [b,t,H,W]. */
+int pf_zsplat_forward_frames(const float* depth_dev, const uint8_t* mask_dev, const uint8_t* seg_dev,
+                             const float* K_dev, const float* Kinv_dev,
+                             const float* E_dev, const float* Einv_dev, const float* T_dev,
+                             int b, int t, int H, int W, int payload,
+                             const uint8_t* lut_dev,
+                             uint8_t* out_seg_dev, float* out_depth_dev, int64_t* out_coords_dev,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Same, with HOST buffers: copies inputs to the device, runs, copies seg/depth back and
  * synchronises the stream.  This is the end-to-end call bench.py times as `e2e`. */
 int pf_zsplat_forward_host(const float* depth, const uint8_t* mask, const uint8_t* seg,
@@ -124,6 +138,15 @@ int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* de
 /* number of kernel launches one pf_bgnet_forward enqueues (for bench.py's gpu_launches) */
 int pf_bgnet_launches_per_forward(const pf_bgnet_t* net);
 int pf_zsplat_launches_per_forward(void);
+
+/* Per-step device timing (CUDA events recorded on the caller's stream around every step of the
+ * next `max_iters` forwards); pf_bgnet_read_profile synchronises on the last event and returns
+ * the number of profiled forwards, with the mean milliseconds of each step in ms_per_step.
+ * step types: 0 first conv (labels), 1 ConvLayer, 2 avg-pool, 3 bilinear upsample, 4 head. */
+int pf_bgnet_set_profiling(pf_bgnet_t* net, int max_iters);
+int pf_bgnet_num_steps(const pf_bgnet_t* net);
+int pf_bgnet_step_info(const pf_bgnet_t* net, int k, int* type, int* conv_index);
+int pf_bgnet_read_profile(pf_bgnet_t* net, float* ms_per_step, int cap);
 
 /* Layer-level debug/test hooks: run ONE ConvLayer i on an NCHW fp32 device tensor. */
 int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_dev, int b, int H, int W,

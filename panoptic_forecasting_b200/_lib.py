@@ -26,6 +26,7 @@ SIGNATURES = {
     "pf_last_error": (C.c_char_p, []),
     "pf_zsplat_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "pf_zsplat_forward": (_i, [_vp] * 8 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
+    "pf_zsplat_forward_frames": (_i, [_vp] * 8 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
     "pf_zsplat_forward_host": (_i, [_vp] * 8 + [_i] * 5 + [_vp] * 3),
     "pf_zsplat_launches_per_forward": (_i, []),
     "pf_depth_disk_hop": (_i, [_vp, _vp, _vp, _sz, _f, _f, _vp]),
@@ -39,6 +40,10 @@ SIGNATURES = {
     "pf_bgnet_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "pf_bgnet_forward": (_i, [_vp] * 4 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
     "pf_bgnet_launches_per_forward": (_i, [_vp]),
+    "pf_bgnet_set_profiling": (_i, [_vp, _i]),
+    "pf_bgnet_num_steps": (_i, [_vp]),
+    "pf_bgnet_step_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "pf_bgnet_read_profile": (_i, [_vp, C.POINTER(_f), _i]),
     "pf_bgnet_debug_conv": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "pf_upsample_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }

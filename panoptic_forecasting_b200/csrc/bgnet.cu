@@ -71,6 +71,9 @@ struct pf_bgnet {
   float* first_tab_dev = nullptr;
   size_t first_tab_floats = 0;
   int launches = 0;
+  // optional per-step CUDA-event profiling (bench.py roofline): ring of [iters][steps+1] events
+  std::vector<cudaEvent_t> prof_ev;
+  int prof_cap = 0, prof_iter = 0;
 
   int new_buf(int shift, int cstride) {
     BufDesc b;
@@ -508,6 +511,7 @@ extern "C" void pf_bgnet_destroy(pf_bgnet_t* net) {
     if (c.bias_dev) cudaFree(c.bias_dev);
   }
   if (net->first_tab_dev) cudaFree(net->first_tab_dev);
+  for (auto e : net->prof_ev) cudaEventDestroy(e);
   delete net;
 }
 
@@ -674,7 +678,13 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
   Arena a;
   make_arena(net, workspace_dev, b, H, W, &a);
 
+  const int nsteps = (int)net->steps.size();
+  const bool prof = net->prof_iter < net->prof_cap;
+  cudaEvent_t* pev = prof ? &net->prof_ev[(size_t)net->prof_iter * (nsteps + 1)] : nullptr;
+  int step_i = 0;
   for (const Step& s : net->steps) {
+    if (prof) PF_CHECK_CUDA(cudaEventRecord(pev[step_i], st));
+    ++step_i;
     switch (s.type) {
       case STEP_FIRST: {
         const ConvDesc& c = net->convs[s.conv];
@@ -766,7 +776,46 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
       }
     }
   }
+  if (prof) {
+    PF_CHECK_CUDA(cudaEventRecord(pev[nsteps], st));
+    net->prof_iter++;
+  }
   return 0;
+}
+
+extern "C" int pf_bgnet_set_profiling(pf_bgnet_t* net, int max_iters) {
+  PF_REQUIRE(net && max_iters >= 0, PF_EINVAL, "pf_bgnet_set_profiling: bad argument");
+  for (auto e : net->prof_ev) cudaEventDestroy(e);
+  net->prof_ev.clear();
+  net->prof_cap = max_iters; net->prof_iter = 0;
+  const size_t n = (size_t)max_iters * (net->steps.size() + 1);
+  net->prof_ev.resize(n);
+  for (size_t i = 0; i < n; ++i) PF_CHECK_CUDA(cudaEventCreate(&net->prof_ev[i]));
+  return 0;
+}
+
+extern "C" int pf_bgnet_num_steps(const pf_bgnet_t* net) { return net ? (int)net->steps.size() : PF_EINVAL; }
+
+extern "C" int pf_bgnet_step_info(const pf_bgnet_t* net, int k, int* type, int* conv_index) {
+  PF_REQUIRE(net && type && conv_index && k >= 0 && k < (int)net->steps.size(), PF_EINVAL, "pf_bgnet_step_info: bad index");
+  *type = (int)net->steps[k].type; *conv_index = net->steps[k].conv;
+  return 0;
+}
+
+extern "C" int pf_bgnet_read_profile(pf_bgnet_t* net, float* ms_per_step, int cap) {
+  PF_REQUIRE(net && ms_per_step, PF_EINVAL, "pf_bgnet_read_profile: null pointer");
+  const int nsteps = (int)net->steps.size();
+  PF_REQUIRE(cap >= nsteps, PF_EINVAL, "pf_bgnet_read_profile: cap < num_steps");
+  for (int k = 0; k < nsteps; ++k) ms_per_step[k] = 0.f;
+  if (net->prof_iter == 0) return 0;
+  PF_CHECK_CUDA(cudaEventSynchronize(net->prof_ev[(size_t)(net->prof_iter - 1) * (nsteps + 1) + nsteps]));
+  for (int it = 0; it < net->prof_iter; ++it)
+    for (int k = 0; k < nsteps; ++k) {
+      float ms = 0.f;
+      PF_CHECK_CUDA(cudaEventElapsedTime(&ms, net->prof_ev[(size_t)it * (nsteps + 1) + k], net->prof_ev[(size_t)it * (nsteps + 1) + k + 1]));
+      ms_per_step[k] += ms / net->prof_iter;
+    }
+  return net->prof_iter;
 }
 
 extern "C" int pf_upsample_argmax(const float* logits_nchw_dev, int b, int classes, int h, int w, int final_h,

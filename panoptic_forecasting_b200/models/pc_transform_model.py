@@ -45,10 +45,15 @@ class PCTransformModel(BaseModel):
             raise TypeError("seg must be uint8 (reference dataset dtype), got %s" % segs.dtype)
         # The reference inverts K / E with torch.inverse (:51,:71).  Optional precomputed inverses
         # (e.g. from the CPU, for bit parity with a CPU run of the reference) may be supplied.
-        K = K.to(dev, torch.float32)
-        E = extrinsics.to(dev, torch.float32)
+        K = K.to(dev, torch.float32).contiguous()
+        E = extrinsics.to(dev, torch.float32).contiguous()
         Kinv = inputs['intrinsics_inv'].to(dev, torch.float32) if 'intrinsics_inv' in inputs else torch.inverse(K)
         Einv = inputs['extrinsics_inv'].to(dev, torch.float32) if 'extrinsics_inv' in inputs else torch.inverse(E)
+        # torch.inverse returns column-major batches: materialise row-major copies and KEEP the
+        # references alive until the launch is enqueued (a temporary would be recycled by the
+        # caching allocator before the kernel reads it).
+        Kinv = Kinv.contiguous()
+        Einv = Einv.contiguous()
         depth_c = depths.to(torch.float32).contiguous()
         mask_c = depth_mask.to(torch.uint8).contiguous()
         seg_c = segs.contiguous()
@@ -67,8 +72,7 @@ class PCTransformModel(BaseModel):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = L.pf_zsplat_forward(depth_c.data_ptr(), mask_c.data_ptr(), seg_c.data_ptr(),
-                                     K.contiguous().data_ptr(), Kinv.contiguous().data_ptr(),
-                                     E.contiguous().data_ptr(), Einv.contiguous().data_ptr(), T_c.data_ptr(),
+                                     K.data_ptr(), Kinv.data_ptr(), E.data_ptr(), Einv.data_ptr(), T_c.data_ptr(),
                                      b, t, H, W, payload, _lib.ptr(lut),
                                      out_seg.data_ptr(), out_depth.data_ptr(), _lib.ptr(coords),
                                      ws.data_ptr(), ws.numel(), stream)

@@ -1,0 +1,86 @@
+"""Composite bg-forecast path: per-frame reprojection (Stage A) -> disk-hop emulation -> BGModel
+(Stage B), all on the device.
+
+The reference runs these as two separate exports joined through PNG / HDF5 files
+(SURVEY.md section 3.1/3.2): `task: pc_transform` with model.only_this_ind = 0,1,2 writes label
+PNGs and uint16 depth PNGs (experiments/export_cityscapes_segmentation_results.py:107-124);
+`task: bg` reads them back (data/datasets/bg_dataset.py:172-232).  This class keeps the same
+arithmetic (including the 1/256 m depth quantisation of the disk format) without the disk.
+"""
+import torch
+
+from . import _lib
+from .models.bg_model import BGModel
+
+
+class BGForecastPipeline:
+    def __init__(self, bg_model, min_depth=None, max_depth=None, emulate_disk_hop=True):
+        assert isinstance(bg_model, BGModel)
+        self.bg = bg_model
+        self.min_depth = bg_model.min_depth if min_depth is None else min_depth
+        self.max_depth = bg_model.max_depth if max_depth is None else max_depth
+        self.emulate_disk_hop = emulate_disk_hop
+        self._lib = _lib.lib()
+        self._ws = None
+
+    def warp(self, inputs):
+        """All t frames reprojected into the target frame, each in its own z-buffer
+        (== t reference PCTransformModel.predict calls with only_this_ind = 0..t-1).
+        Returns (seg u8 [b,t,H,W], depth f32 [b,t,H,W])."""
+        depth = inputs['depth']
+        if not depth.is_cuda:
+            raise _lib.PFError("BGForecastPipeline needs CUDA tensors (no CPU fallback)")
+        dev = depth.device
+        b, t, H, W = depth.shape
+        K = inputs['intrinsics'].to(dev, torch.float32).contiguous()
+        E = inputs['extrinsics'].to(dev, torch.float32).contiguous()
+        Kinv = (inputs['intrinsics_inv'].to(dev, torch.float32) if 'intrinsics_inv' in inputs
+                else torch.inverse(K)).contiguous()
+        Einv = (inputs['extrinsics_inv'].to(dev, torch.float32) if 'extrinsics_inv' in inputs
+                else torch.inverse(E)).contiguous()
+        T = inputs['target_T'].to(dev, torch.float32).contiguous()
+        depth_c = depth.to(torch.float32).contiguous()
+        mask = inputs['depth_mask'].contiguous()
+        mask_c = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+        seg_c = inputs['seg'].contiguous()
+        if seg_c.dtype != torch.uint8:
+            raise TypeError("seg must be uint8")
+        nbytes = self._lib.pf_zsplat_workspace_bytes(b, t, H, W)
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out_seg = torch.empty((b, t, H, W), dtype=torch.uint8, device=dev)
+        out_depth = torch.empty((b, t, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = self._lib.pf_zsplat_forward_frames(
+                depth_c.data_ptr(), mask_c.data_ptr(), seg_c.data_ptr(), K.data_ptr(), Kinv.data_ptr(),
+                E.data_ptr(), Einv.data_ptr(), T.data_ptr(), b, t, H, W, 1, None,
+                out_seg.data_ptr(), out_depth.data_ptr(), None, self._ws.data_ptr(), self._ws.numel(), stream)
+        _lib.check(rc, "pf_zsplat_forward_frames")
+        return out_seg, out_depth
+
+    def decode_depth(self, depth):
+        """Exporter uint16 quantisation + BGDataset decode/clamp, or (emulate_disk_hop=False) only
+        the dataset's mask/clamp rule on the raw warped depth."""
+        dev = depth.device
+        out = torch.empty_like(depth)
+        mask = torch.empty(depth.shape, dtype=torch.uint8, device=dev)
+        if self.emulate_disk_hop:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                rc = self._lib.pf_depth_disk_hop(depth.data_ptr(), out.data_ptr(), mask.data_ptr(), depth.numel(),
+                                                 float(self.min_depth), float(self.max_depth), stream)
+            _lib.check(rc, "pf_depth_disk_hop")
+            return out, mask
+        m = depth > 0
+        d = torch.where(m, depth.clamp(self.min_depth, self.max_depth), torch.full_like(depth, -1))
+        return d, m.to(torch.uint8)
+
+    def forecast(self, inputs):
+        """inputs: the PCTransformModel input dict (pc_transform_model.py:27-32).
+        Returns the BGModel.predict dict plus 'warped_seg' / 'warped_depth' / 'warped_mask'."""
+        seg, depth = self.warp(inputs)
+        d, m = self.decode_depth(depth)
+        out = self.bg.predict({'seg': seg, 'depth': d, 'depth_mask': m}, {})
+        out['warped_seg'], out['warped_depth'], out['warped_mask'] = seg, d, m
+        return out

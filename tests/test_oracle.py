@@ -99,3 +99,18 @@ def test_oracles_match_live_reference():
     out = bg_oracle.predict(sd, x, (128, 256))
     assert torch.equal(out["seg"], ref["seg"])
     assert (out["logits"] - ref["logits"]).abs().max() <= 1e-5 * ref["logits"].abs().max()
+
+
+def test_cpu_port_matches_numpy_oracle():
+    """The torch-CPU baseline port (bench.py's cpu_baseline / --impl reference) agrees bit for bit
+    with the numpy oracle on labels and depths."""
+    from oracle import cpu_port
+    inp = synthetic.make_pc_inputs(b=2, t=3, h=64, w=96, dist="R", seed=8)
+    npin = {k: v.numpy() for k, v in inp.items()}
+    npin["intrinsics_inv"] = torch.inverse(inp["intrinsics"]).numpy()
+    npin["extrinsics_inv"] = torch.inverse(inp["extrinsics"]).numpy()
+    for ind in (0, None):
+        a = cpu_port.pc_predict(inp, only_this_ind=ind)
+        b = pc_transform_oracle.predict(npin, only_this_ind=ind)
+        assert np.array_equal(a["seg"].numpy(), b["seg"])
+        assert np.array_equal(a["depth"].numpy().view(np.uint32), b["depth"].view(np.uint32))

@@ -1,0 +1,53 @@
+"""GPU parity of the composite path (Stage A per frame -> disk hop -> Stage B) vs the composite
+oracle of SURVEY.md section 8c."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bg_params
+from oracle import bg_oracle, pc_transform_oracle
+from panoptic_forecasting_b200 import synthetic
+from panoptic_forecasting_b200.models import build_model
+from panoptic_forecasting_b200.pipeline import BGForecastPipeline
+from test_bgnet_gpu import check_against
+
+pytestmark = pytest.mark.gpu
+
+
+def disk_hop_np(d, mn=0.1, mx=200.0):
+    """export_cityscapes_segmentation_results.py:119-122 then bg_dataset.py:223-230,166-170."""
+    q = ((torch.from_numpy(d) + 1).clamp(0, 255) * 256).round().numpy().astype(np.uint16)
+    r = torch.from_numpy(q.astype(np.float32)) / 256.0 - 1
+    m = r > 0
+    r[~m] = -1
+    r[m & (r > mx)] = mx
+    r[m & (r < mn)] = mn
+    return r, m
+
+
+@pytest.mark.parametrize("b,h,w", [(1, 128, 256), (2, 64, 128)])
+def test_composite_matches_composite_oracle(pf_lib, bg_shapes, b, h, w):
+    pc_in = synthetic.make_pc_inputs(b=b, t=3, h=h, w=w, dist="R", seed=21)
+    npin = {k: v.numpy() for k, v in pc_in.items()}
+    npin["intrinsics_inv"] = torch.inverse(pc_in["intrinsics"]).numpy()
+    npin["extrinsics_inv"] = torch.inverse(pc_in["extrinsics"]).numpy()
+    segs, deps, masks = [], [], []
+    for ind in range(3):
+        r = pc_transform_oracle.predict(npin, only_this_ind=ind)
+        d, m = disk_hop_np(r["depth"])
+        segs.append(torch.from_numpy(r["seg"])); deps.append(d); masks.append(m)
+    bg_in = {"seg": torch.stack(segs, 1).long(), "depth": torch.stack(deps, 1), "depth_mask": torch.stack(masks, 1)}
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=21)
+    q = bg_oracle.predict(sd, bg_in, None)["orig_size_logits"]
+    sd["model.finalConv.bias"] = sd["model.finalConv.bias"] - q.mean((0, 2, 3))
+    ref = bg_oracle.predict(sd, bg_in, None)
+
+    bg = build_model(dict(bg_params(), no_gpu=False)).eval()
+    bg.load_state_dict(sd)
+    pipe = BGForecastPipeline(bg)
+    cu = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in npin.items()}
+    out = pipe.forecast(cu)
+    assert torch.equal(out["warped_seg"].cpu().long(), bg_in["seg"])              # bit-exact stage A
+    assert torch.equal(out["warped_depth"].cpu(), bg_in["depth"])
+    assert torch.equal(out["warped_mask"].cpu().bool(), bg_in["depth_mask"])
+    check_against(out, ref, rel_tol=1e-4)
