@@ -5,7 +5,7 @@
 // Layout: every activation is fp32 NHWC inside one caller-provided arena; every HarDBlock owns a
 // single buffer whose channel slots are [block input | layer1 | layer2 | ...], so the reference's
 // torch.cat calls disappear: a consumer reads a list of channel slices (SegRef), a producer writes
-// its slice.  Slots are aligned/padded to 8 channels; producers write zeros into the pad channels.
+// its slice.  Slots are aligned/padded to 16 channels; producers write zeros into the pad channels.
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "bgnet.h"
+#include "conv_tc.h"
+#include "split_bf16.cuh"
 
 namespace pf {
 
@@ -52,7 +54,7 @@ static void get_link(int layer, int base_ch, int gr, int* out_ch, std::vector<in
   if (link) *link = lk;
 }
 
-static int pad8(int c) { return (c + kChanAlign - 1) / kChanAlign * kChanAlign; }
+static int padc(int c) { return (c + kChanAlign - 1) / kChanAlign * kChanAlign; }
 
 }  // namespace pf
 
@@ -71,6 +73,19 @@ struct pf_bgnet {
   float* first_tab_dev = nullptr;
   size_t first_tab_floats = 0;
   int launches = 0;
+  // tensor-core path (precision 1): packed split-bf16 weights live in ConvDesc-indexed arrays; the
+  // TMA tensor maps depend on the arena address and shape, so they are cached per (ws, b, H, W).
+  std::vector<__nv_bfloat16*> wtc_dev;      // per conv: hi [nrows][ktot] then lo [nrows][ktot]
+  std::vector<int> wtc_rows;
+  struct TcPlan {
+    const void* ws = nullptr; int b = 0, H = 0, W = 0;
+    CUtensorMap* maps_dev = nullptr;
+    std::vector<TcLayer> layers;             // indexed by conv
+    std::vector<int> nblocks;
+    std::vector<size_t> smem;
+    std::vector<char> use_tc;
+  } plan;
+  bool force_simt = false;                   // PF_TC_FORCE_SIMT=1: run every conv on the SIMT kernels (A/B checks)
   // optional per-step CUDA-event profiling (bench.py roofline): ring of [iters][steps+1] events
   std::vector<cudaEvent_t> prof_ev;
   int prof_cap = 0, prof_iter = 0;
@@ -104,7 +119,7 @@ static void build_block(pf_bgnet* net, const std::string& prefix, int in_ch, int
   ch[0] = in_ch;
   for (int l = 1; l <= n_layers; ++l) get_link(l, in_ch, gr, &ch[l], nullptr);
   int total = 0;
-  for (int l = 0; l <= n_layers; ++l) { off[l] = total; total += pad8(ch[l]); }
+  for (int l = 0; l <= n_layers; ++l) { off[l] = total; total += padc(ch[l]); }
   const int buf = net->new_buf(shift, total);
   in_slot->buf = buf; in_slot->coff = 0; in_slot->c = in_ch;
   for (int l = 1; l <= n_layers; ++l) {
@@ -136,9 +151,9 @@ static void build_topology(pf_bgnet* net) {
   const int t = net->num_inputs;
   const int cin0 = (net->num_classes + (net->use_depth ? 1 : 0)) * t;
   // stem (hardnet.py:275-280)
-  int s0 = net->new_buf(1, pad8(kFirstCh[0]));
-  int s1 = net->new_buf(1, pad8(kFirstCh[1]));
-  int s2 = net->new_buf(2, pad8(kFirstCh[2]));
+  int s0 = net->new_buf(1, padc(kFirstCh[0]));
+  int s1 = net->new_buf(1, padc(kFirstCh[1]));
+  int s2 = net->new_buf(2, padc(kFirstCh[2]));
   SegRef r0{s0, 0, kFirstCh[0]}, r1{s1, 0, kFirstCh[1]}, r2{s2, 0, kFirstCh[2]};
   {
     int ci = net->add_conv("model.base.0", cin0, kFirstCh[0], 3, 2, {}, r0);
@@ -175,7 +190,7 @@ static void build_topology(pf_bgnet* net) {
     // 1x1 transition (hardnet.py:292)
     snprintf(pfx, sizeof(pfx), "model.base.%d", idx);
     idx++;
-    int pbuf = net->new_buf(shift, pad8(kChList[i]));
+    int pbuf = net->new_buf(shift, padc(kChList[i]));
     SegRef pout{pbuf, 0, kChList[i]};
     int ci = net->add_conv(pfx, oc, kChList[i], 1, 1, outs, pout);
     { Step st; st.type = STEP_CONV; st.conv = ci; net->steps.push_back(st); }
@@ -238,7 +253,9 @@ constexpr int F_IH = F_TH * 2 + 1, F_IW = F_TW * 2 + 1;
 struct FirstParams {
   const uint8_t* labels; const float* depth; const uint8_t* mask;
   const float* tab;    // lut | wd | bias
-  float* out;          // NHWC, 16 channels
+  void* out;           // NHWC, 16 channels: fp32, or bf16 hi plane
+  void* out_lo;        // bf16 lo plane (split storage)
+  int split;
   int b, t, H, W, Ho, Wo, ncls, use_depth;
   float mean, std;
 };
@@ -310,36 +327,44 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(FirstParams p) {
   }
   const int oy = oy0 + py, ox = ox0 + px;
   if (oy < p.Ho && ox < p.Wo) {
-    float4* o = reinterpret_cast<float4*>(p.out + (((size_t)img * p.Ho + oy) * p.Wo + ox) * 16);
+    const size_t o = (((size_t)img * p.Ho + oy) * p.Wo + ox) * 16;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      o[q] = make_float4(fmaxf(acc[q * 4 + 0], 0.f), fmaxf(acc[q * 4 + 1], 0.f), fmaxf(acc[q * 4 + 2], 0.f),
-                         fmaxf(acc[q * 4 + 3], 0.f));
+      store4_any(p.out, p.out_lo, o + q * 4,
+                 make_float4(fmaxf(acc[q * 4 + 0], 0.f), fmaxf(acc[q * 4 + 1], 0.f), fmaxf(acc[q * 4 + 2], 0.f),
+                             fmaxf(acc[q * 4 + 3], 0.f)),
+                 p.split != 0);
   }
 }
 
 // AvgPool2d(2,2) (hardnet.py:296) NHWC slice -> NHWC slice, 4 channels per thread.
-__global__ void avgpool2_kernel(const float* __restrict__ in, int in_cs, size_t in_img, float* __restrict__ out,
-                                int out_cs, size_t out_img, int b, int Ho, int Wo, int c4) {
-  const size_t total = (size_t)b * Ho * Wo * c4;
+struct PoolParams {
+  const void* in; const void* in_lo; int in_cs; size_t in_img;
+  void* out; void* out_lo; int out_cs; size_t out_img;
+  int b, Ho, Wo, c4, split;
+};
+
+__global__ void avgpool2_kernel(PoolParams p) {
+  const size_t total = (size_t)p.b * p.Ho * p.Wo * p.c4;
+  const bool sp = p.split != 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4);
-    size_t r = i / c4;
-    const int x = (int)(r % Wo); r /= Wo;
-    const int y = (int)(r % Ho);
-    const int img = (int)(r / Ho);
-    const int Wi = Wo * 2;
-    const float* p0 = in + img * in_img + ((size_t)(2 * y) * Wi + 2 * x) * in_cs + c * 4;
-    const float4 a = *reinterpret_cast<const float4*>(p0);
-    const float4 bq = *reinterpret_cast<const float4*>(p0 + in_cs);
-    const float4 cq = *reinterpret_cast<const float4*>(p0 + (size_t)Wi * in_cs);
-    const float4 d = *reinterpret_cast<const float4*>(p0 + (size_t)Wi * in_cs + in_cs);
+    const int c = (int)(i % p.c4);
+    size_t r = i / p.c4;
+    const int x = (int)(r % p.Wo); r /= p.Wo;
+    const int y = (int)(r % p.Ho);
+    const int img = (int)(r / p.Ho);
+    const int Wi = p.Wo * 2;
+    const size_t p0 = img * p.in_img + ((size_t)(2 * y) * Wi + 2 * x) * p.in_cs + c * 4;
+    const float4 a = load4_any(p.in, p.in_lo, p0, sp);
+    const float4 bq = load4_any(p.in, p.in_lo, p0 + p.in_cs, sp);
+    const float4 cq = load4_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs, sp);
+    const float4 d = load4_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs + p.in_cs, sp);
     float4 o;
     o.x = (a.x + bq.x + cq.x + d.x) * 0.25f;
     o.y = (a.y + bq.y + cq.y + d.y) * 0.25f;
     o.z = (a.z + bq.z + cq.z + d.z) * 0.25f;
     o.w = (a.w + bq.w + cq.w + d.w) * 0.25f;
-    *reinterpret_cast<float4*>(out + img * out_img + ((size_t)y * Wo + x) * out_cs + c * 4) = o;
+    store4_any(p.out, p.out_lo, img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + c * 4, o, sp);
   }
 }
 
@@ -349,13 +374,14 @@ struct UpParams {
   SegView segs[kMaxSegs];
   size_t in_img[kMaxSegs];
   int nseg;
-  float* out; int out_cs; size_t out_img;
-  int b, Hi, Wi, Ho, Wo, c4_total;
+  void* out; void* out_lo; int out_cs; size_t out_img;
+  int b, Hi, Wi, Ho, Wo, c4_total, split;
   float sh, sw;
 };
 
 __global__ void upsample_bilinear_kernel(UpParams p) {
   const size_t total = (size_t)p.b * p.Ho * p.Wo * p.c4_total;
+  const bool sp = p.split != 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(i % p.c4_total) * 4;
     size_t r = i / p.c4_total;
@@ -370,18 +396,20 @@ __global__ void upsample_bilinear_kernel(UpParams p) {
     const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
     const float ly = fy - (float)y0, lx = fx - (float)x0;
     const float hy = 1.f - ly, hx = 1.f - lx;
-    const float* base = p.segs[s].base + img * p.in_img[s] + c;
+    const size_t base = img * p.in_img[s] + c;
     const int cs = p.segs[s].cstride;
-    const float4 v00 = *reinterpret_cast<const float4*>(base + ((size_t)y0 * p.Wi + x0) * cs);
-    const float4 v01 = *reinterpret_cast<const float4*>(base + ((size_t)y0 * p.Wi + x1) * cs);
-    const float4 v10 = *reinterpret_cast<const float4*>(base + ((size_t)y1 * p.Wi + x0) * cs);
-    const float4 v11 = *reinterpret_cast<const float4*>(base + ((size_t)y1 * p.Wi + x1) * cs);
+    const void* bh = p.segs[s].base;
+    const void* bl = p.segs[s].base_lo;
+    const float4 v00 = load4_any(bh, bl, base + ((size_t)y0 * p.Wi + x0) * cs, sp);
+    const float4 v01 = load4_any(bh, bl, base + ((size_t)y0 * p.Wi + x1) * cs, sp);
+    const float4 v10 = load4_any(bh, bl, base + ((size_t)y1 * p.Wi + x0) * cs, sp);
+    const float4 v11 = load4_any(bh, bl, base + ((size_t)y1 * p.Wi + x1) * cs, sp);
     float4 o;
     o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
     o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
     o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
     o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    *reinterpret_cast<float4*>(p.out + img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + cout) = o;
+    store4_any(p.out, p.out_lo, img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + cout, o, sp);
   }
 }
 
@@ -438,9 +466,9 @@ __global__ void nhwc16_to_nchw_kernel(const float* __restrict__ q, float* __rest
   }
 }
 
-// debug helpers: NCHW <-> NHWC(slice)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int b, int c, int h, int w,
-                                    int cs) {
+// debug helpers: NCHW fp32 <-> NHWC (fp32 or split-bf16) with channel stride cs
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, void* out, void* out_lo, int split, int b, int c,
+                                    int h, int w, int cs) {
   const size_t total = (size_t)b * h * w * cs;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % cs);
@@ -448,11 +476,19 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
     const int x = (int)(r % w); r /= w;
     const int y = (int)(r % h);
     const int img = (int)(r / h);
-    out[i] = ch < c ? in[(((size_t)img * c + ch) * h + y) * w + x] : 0.f;
+    const float v = ch < c ? in[(((size_t)img * c + ch) * h + y) * w + x] : 0.f;
+    if (!split) {
+      reinterpret_cast<float*>(out)[i] = v;
+    } else {
+      unsigned hi, lo;
+      split1(v, &hi, &lo);
+      reinterpret_cast<unsigned short*>(out)[i] = (unsigned short)hi;
+      reinterpret_cast<unsigned short*>(out_lo)[i] = (unsigned short)lo;
+    }
   }
 }
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int b, int c, int h, int w,
-                                    int cs) {
+__global__ void nhwc_to_nchw_kernel(const void* in, const void* in_lo, int split, float* __restrict__ out, int b,
+                                    int c, int h, int w, int cs) {
   const size_t total = (size_t)b * c * h * w;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
@@ -460,7 +496,14 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
     const int y = (int)(r % h); r /= h;
     const int ch = (int)(r % c);
     const int img = (int)(r / c);
-    out[i] = in[(((size_t)img * h + y) * w + x) * cs + ch];
+    const size_t o = (((size_t)img * h + y) * w + x) * cs + ch;
+    if (!split) {
+      out[i] = reinterpret_cast<const float*>(in)[o];
+    } else {
+      const unsigned hi = reinterpret_cast<const unsigned short*>(in)[o];
+      const unsigned lo = reinterpret_cast<const unsigned short*>(in_lo)[o];
+      out[i] = __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
+    }
   }
 }
 
@@ -472,17 +515,221 @@ static int grid_for(size_t total, int threads) {
   return (int)g;
 }
 
-static size_t plan_offsets(const pf_bgnet* net, int H, int W, std::vector<size_t>* img_floats) {
-  // returns total floats per image; buffers laid out back to back (256-byte aligned)
+// ------------------------------------------------------------------------------------------
+// Arena: all activation buffers of one forward inside the caller's work space.
+// fp32 storage: one plane per buffer; split storage: a bf16 hi plane followed by a bf16 lo plane.
+// The quarter-resolution logits buffer is always fp32.
+struct Arena {
+  char* base = nullptr;
+  int b = 0, H = 0, W = 0;
+  bool split = false;
+  std::vector<size_t> off;        // byte offset of the (hi) plane of each buffer
+  std::vector<size_t> off_lo;     // byte offset of the lo plane (split storage)
+  std::vector<size_t> img_elems;  // elements between consecutive images of a buffer
+  size_t total_bytes = 0;
+
+  void* ptr(int buf, int coff) const { return base + off[buf] + (size_t)coff * (split_buf(buf) ? 2 : 4); }
+  void* ptr_lo(int buf, int coff) const { return split_buf(buf) ? base + off_lo[buf] + (size_t)coff * 2 : nullptr; }
+  bool split_buf(int buf) const { return split && buf != quarter; }
+  int quarter = -1;
+};
+
+static void make_arena(const pf_bgnet* net, void* ws, int b, int H, int W, Arena* a) {
+  a->base = ws ? reinterpret_cast<char*>(align_up((size_t)ws, 256)) : nullptr;
+  a->b = b; a->H = H; a->W = W;
+  a->split = net->precision == 1;
+  a->quarter = net->quarter_buf;
+  const size_t nb = net->bufs.size();
+  a->off.resize(nb); a->off_lo.resize(nb); a->img_elems.resize(nb);
   size_t off = 0;
-  img_floats->resize(net->bufs.size());
-  for (size_t i = 0; i < net->bufs.size(); ++i) {
+  for (size_t i = 0; i < nb; ++i) {
     const BufDesc& bd = net->bufs[i];
-    size_t n = (size_t)(H >> bd.shift) * (W >> bd.shift) * bd.cstride;
-    (*img_floats)[i] = n;
-    off += align_up(n, 64);
+    const size_t n = align_up((size_t)(H >> bd.shift) * (W >> bd.shift) * bd.cstride, 64);
+    a->img_elems[i] = n;
+    const bool sp = a->split_buf((int)i);
+    a->off[i] = off;
+    off += align_up(n * b * (sp ? 2 : 4), 256);
+    if (sp) {
+      a->off_lo[i] = off;
+      off += align_up(n * b * 2, 256);
+    }
   }
-  return off;
+  a->total_bytes = off + 256;
+}
+
+static void fill_conv_launch(const pf_bgnet* net, const Arena& a, const ConvDesc& c, ConvLaunch* L) {
+  L->nseg = (int)c.in.size();
+  for (int s = 0; s < L->nseg; ++s) {
+    const SegRef& r = c.in[s];
+    L->segs[s].base = a.ptr(r.buf, r.coff);
+    L->segs[s].base_lo = a.ptr_lo(r.buf, r.coff);
+    L->segs[s].cstride = net->bufs[r.buf].cstride;
+    L->segs[s].cpad = r.cpad();
+    L->in_img_stride[s] = a.img_elems[r.buf];
+  }
+  const BufDesc& ib = net->bufs[c.in[0].buf];
+  const BufDesc& ob = net->bufs[c.out.buf];
+  L->b = a.b;
+  L->Hin = a.H >> ib.shift; L->Win = a.W >> ib.shift;
+  L->Hout = a.H >> ob.shift; L->Wout = a.W >> ob.shift;
+  L->out = a.ptr(c.out.buf, c.out.coff);
+  L->out_lo = a.ptr_lo(c.out.buf, c.out.coff);
+  L->out_cstride = ob.cstride;
+  L->out_img_stride = a.img_elems[c.out.buf];
+  L->w = c.w_dev; L->bias = c.bias_dev;
+  L->kpad = c.kpad; L->coutpad = c.coutpad;
+  L->cout_store = padc(c.cout);
+  L->relu = c.relu ? 1 : 0;
+}
+
+// ---- tensor-core path helpers --------------------------------------------------------------
+static unsigned short f32_to_bf16_rn(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (unsigned short)(u >> 16);   // inf / nan
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (unsigned short)(u >> 16);
+}
+static float bf16_to_f32(unsigned short h) {
+  unsigned u = (unsigned)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// Packs the folded fp32 weights of conv i as the K-major B operand: W[n][k], k = seg_base +
+// tap * cpad(seg) + channel, split into bf16 hi / lo planes.
+static int upload_conv_tc(pf_bgnet* net, int i) {
+  ConvDesc& c = net->convs[i];
+  if (net->wtc_dev.size() < net->convs.size()) {
+    net->wtc_dev.resize(net->convs.size(), nullptr);
+    net->wtc_rows.resize(net->convs.size(), 0);
+  }
+  const int taps = c.ksize * c.ksize;
+  const int ktot = taps * c.kpad;
+  int ntile, nblocks, stages, cols;
+  size_t smem;
+  tc_pick_tiling(c.coutpad, &ntile, &nblocks, &stages, &cols, &smem);
+  const int nrows = ntile * nblocks;
+  std::vector<unsigned short> w((size_t)2 * nrows * ktot, 0);
+  int kp = 0, kb = 0;
+  for (auto& s : c.in) {
+    const int cp = s.cpad();
+    for (int tap = 0; tap < taps; ++tap)
+      for (int ch = 0; ch < s.c; ++ch)
+        for (int o = 0; o < c.cout; ++o) {
+          const float v = c.w_host[((size_t)tap * c.kpad + kp + ch) * c.coutpad + o];
+          const unsigned short hi = f32_to_bf16_rn(v);
+          const unsigned short lo = f32_to_bf16_rn(v - bf16_to_f32(hi));
+          const size_t k = (size_t)kb + (size_t)tap * cp + ch;
+          w[(size_t)o * ktot + k] = hi;
+          w[(size_t)nrows * ktot + (size_t)o * ktot + k] = lo;
+        }
+    kp += cp;
+    kb += taps * cp;
+  }
+  if (net->wtc_dev[i]) cudaFree(net->wtc_dev[i]);
+  PF_CHECK_CUDA(cudaMalloc(&net->wtc_dev[i], w.size() * 2));
+  PF_CHECK_CUDA(cudaMemcpy(net->wtc_dev[i], w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+  net->wtc_rows[i] = nrows;
+  return 0;
+}
+
+struct TcIo {                       // where one conv reads and writes (arena or debug buffers)
+  const void* in_hi[kMaxSegs]; const void* in_lo[kMaxSegs];
+  int in_cs[kMaxSegs]; size_t in_img[kMaxSegs];
+  int Hin, Win, Hout, Wout, b;
+  void* out_hi; void* out_lo; float* out_f32; int out_cs; size_t out_img;
+};
+
+// Appends the tensor maps of conv i to `maps` and fills its TcLayer.
+static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUtensorMap>* maps, TcLayer* L,
+                          int* nblocks, size_t* smem) {
+  const ConvDesc& c = net->convs[i];
+  PF_REQUIRE(c.stride == 1, PF_EINVAL, "build_tc_layer: stride-2 convs run on the SIMT kernel");
+  memset(L, 0, sizeof(*L));
+  const int taps = c.ksize * c.ksize;
+  L->nseg = (int)c.in.size();
+  int kb = 0;
+  for (int s = 0; s < L->nseg; ++s) {
+    const int cp = c.in[s].cpad();
+    L->seg_cpad[s] = cp;
+    L->seg_koff[s] = kb;
+    kb += taps * cp;
+    L->seg_map[s] = (int)maps->size();
+    CUtensorMap m;
+    int rc = tc_encode_act_map(&m, io.in_hi[s], cp, io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s]);
+    if (rc) return rc;
+    maps->push_back(m);
+    rc = tc_encode_act_map(&m, io.in_lo[s], cp, io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s]);
+    if (rc) return rc;
+    maps->push_back(m);
+  }
+  const int ktot = taps * c.kpad;
+  int ntile, nb, stages, cols;
+  tc_pick_tiling(c.coutpad, &ntile, &nb, &stages, &cols, smem);
+  *nblocks = nb;
+  const int nrows = net->wtc_rows[i];
+  L->w_map = (int)maps->size();
+  {
+    CUtensorMap m;
+    int rc = tc_encode_weight_map(&m, net->wtc_dev[i], ktot, nrows, ntile);
+    if (rc) return rc;
+    maps->push_back(m);
+    rc = tc_encode_weight_map(&m, net->wtc_dev[i] + (size_t)nrows * ktot, ktot, nrows, ntile);
+    if (rc) return rc;
+    maps->push_back(m);
+  }
+  L->taps = taps; L->ksize = c.ksize;
+  L->Hout = io.Hout; L->Wout = io.Wout;
+  L->tiles_x = cdiv(io.Wout, 16); L->tiles_y = cdiv(io.Hout, 8);
+  L->ntile = ntile; L->stages = stages; L->tmem_cols = cols;
+  L->cout_store = io.out_f32 ? 16 : padc(c.cout);
+  L->relu = c.relu ? 1 : 0;
+  L->out_hi = reinterpret_cast<__nv_bfloat16*>(io.out_hi);
+  L->out_lo = reinterpret_cast<__nv_bfloat16*>(io.out_lo);
+  L->out_f32 = io.out_f32;
+  L->out_cs = io.out_cs; L->out_img_stride = io.out_img;
+  L->bias = c.bias_dev;
+  return 0;
+}
+
+static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
+  auto& P = net->plan;
+  if (P.ws == ws && P.b == a.b && P.H == a.H && P.W == a.W && P.maps_dev) return 0;
+  std::vector<CUtensorMap> maps;
+  const size_t nc = net->convs.size();
+  P.layers.assign(nc, TcLayer());
+  P.nblocks.assign(nc, 0);
+  P.smem.assign(nc, 0);
+  P.use_tc.assign(nc, 0);
+  for (size_t i = 0; i < nc; ++i) {
+    const ConvDesc& c = net->convs[i];
+    if ((int)i == net->first_conv || c.stride != 1) continue;
+    TcIo io;
+    for (size_t s = 0; s < c.in.size(); ++s) {
+      const SegRef& r = c.in[s];
+      io.in_hi[s] = a.ptr(r.buf, r.coff); io.in_lo[s] = a.ptr_lo(r.buf, r.coff);
+      io.in_cs[s] = net->bufs[r.buf].cstride; io.in_img[s] = a.img_elems[r.buf];
+    }
+    const BufDesc& ib = net->bufs[c.in[0].buf];
+    const BufDesc& ob = net->bufs[c.out.buf];
+    io.Hin = a.H >> ib.shift; io.Win = a.W >> ib.shift; io.Hout = a.H >> ob.shift; io.Wout = a.W >> ob.shift; io.b = a.b;
+    const bool head = (int)i == net->final_conv;
+    io.out_hi = head ? nullptr : a.ptr(c.out.buf, c.out.coff);
+    io.out_lo = head ? nullptr : a.ptr_lo(c.out.buf, c.out.coff);
+    io.out_f32 = head ? reinterpret_cast<float*>(a.ptr(c.out.buf, c.out.coff)) : nullptr;
+    io.out_cs = ob.cstride; io.out_img = a.img_elems[c.out.buf];
+    int rc = build_tc_layer(net, (int)i, io, &maps, &P.layers[i], &P.nblocks[i], &P.smem[i]);
+    if (rc) return rc;
+    P.use_tc[i] = 1;
+  }
+  if (P.maps_dev) cudaFree(P.maps_dev);
+  P.maps_dev = nullptr;
+  PF_CHECK_CUDA(cudaMalloc(&P.maps_dev, maps.size() * sizeof(CUtensorMap)));
+  PF_CHECK_CUDA(cudaMemcpy(P.maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  P.ws = ws; P.b = a.b; P.H = a.H; P.W = a.W;
+  return 0;
 }
 
 }  // namespace pf
@@ -499,6 +746,8 @@ extern "C" int pf_bgnet_create(pf_bgnet_t** out, int num_classes, int num_inputs
   pf_bgnet* net = new pf_bgnet();
   net->num_classes = num_classes; net->num_inputs = num_inputs; net->use_depth = use_depth ? 1 : 0;
   net->precision = precision;
+  const char* fs = getenv("PF_TC_FORCE_SIMT");
+  net->force_simt = fs && fs[0] == '1';
   build_topology(net);
   *out = net;
   return 0;
@@ -510,6 +759,8 @@ extern "C" void pf_bgnet_destroy(pf_bgnet_t* net) {
     if (c.w_dev) cudaFree(c.w_dev);
     if (c.bias_dev) cudaFree(c.bias_dev);
   }
+  for (auto p : net->wtc_dev) if (p) cudaFree(p);
+  if (net->plan.maps_dev) cudaFree(net->plan.maps_dev);
   if (net->first_tab_dev) cudaFree(net->first_tab_dev);
   for (auto e : net->prof_ev) cudaEventDestroy(e);
   delete net;
@@ -567,6 +818,11 @@ static int upload_conv(pf_bgnet* net, int i, const std::vector<double>& wfold /*
   if (!c.bias_dev) PF_CHECK_CUDA(cudaMalloc(&c.bias_dev, c.bias_host.size() * sizeof(float)));
   PF_CHECK_CUDA(cudaMemcpy(c.w_dev, c.w_host.data(), c.w_host.size() * sizeof(float), cudaMemcpyHostToDevice));
   PF_CHECK_CUDA(cudaMemcpy(c.bias_dev, c.bias_host.data(), c.bias_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (net->precision == 1) {
+    int rc = upload_conv_tc(net, i);
+    if (rc) return rc;
+    net->plan.ws = nullptr;        // weight addresses may have changed -> re-encode the tensor maps
+  }
   c.loaded = true;
   return 0;
 }
@@ -604,62 +860,29 @@ extern "C" int pf_bgnet_set_depth_norm(pf_bgnet_t* net, float mean, float std) {
 
 extern "C" size_t pf_bgnet_workspace_bytes(const pf_bgnet_t* net, int b, int H, int W) {
   if (!net || b <= 0 || H <= 0 || W <= 0 || H % 64 || W % 64) return 0;
-  std::vector<size_t> img;
-  size_t per_img = plan_offsets(net, H, W, &img);
-  return per_img * b * sizeof(float) + 256;
+  Arena a;
+  make_arena(net, nullptr, b, H, W, &a);
+  return a.total_bytes;
 }
-
-namespace pf {
-
-struct Arena {
-  float* base;
-  int b, H, W;
-  std::vector<size_t> buf_off;   // floats, start of buffer (all images contiguous per buffer)
-  std::vector<size_t> img_floats;
-};
-
-static void make_arena(const pf_bgnet* net, void* ws, int b, int H, int W, Arena* a) {
-  a->base = reinterpret_cast<float*>(align_up((size_t)ws, 256));
-  a->b = b; a->H = H; a->W = W;
-  plan_offsets(net, H, W, &a->img_floats);
-  a->buf_off.resize(net->bufs.size());
-  size_t off = 0;
-  for (size_t i = 0; i < net->bufs.size(); ++i) {
-    a->buf_off[i] = off;
-    off += align_up(a->img_floats[i], 64) * b;
-  }
-}
-
-static void fill_conv_launch(const pf_bgnet* net, const Arena& a, const ConvDesc& c, ConvLaunch* L) {
-  L->nseg = (int)c.in.size();
-  for (int s = 0; s < L->nseg; ++s) {
-    const SegRef& r = c.in[s];
-    L->segs[s].base = a.base + a.buf_off[r.buf] + r.coff;
-    L->segs[s].cstride = net->bufs[r.buf].cstride;
-    L->segs[s].cpad = r.cpad();
-    L->in_img_stride[s] = align_up(a.img_floats[r.buf], 64);
-  }
-  const BufDesc& ib = net->bufs[c.in[0].buf];
-  const BufDesc& ob = net->bufs[c.out.buf];
-  L->b = a.b;
-  L->Hin = a.H >> ib.shift; L->Win = a.W >> ib.shift;
-  L->Hout = a.H >> ob.shift; L->Wout = a.W >> ob.shift;
-  L->out = a.base + a.buf_off[c.out.buf] + c.out.coff;
-  L->out_cstride = ob.cstride;
-  L->out_img_stride = align_up(a.img_floats[c.out.buf], 64);
-  L->w = c.w_dev; L->bias = c.bias_dev;
-  L->kpad = c.kpad; L->coutpad = c.coutpad;
-  L->cout_store = pad8(c.cout);
-  L->relu = c.relu ? 1 : 0;
-}
-
-}  // namespace pf
 
 extern "C" int pf_bgnet_launches_per_forward(const pf_bgnet_t* net) {
   if (!net) return PF_EINVAL;
   int n = 0;
   for (auto& s : net->steps) n += (s.type == STEP_HEAD) ? 2 : 1;
   return n;
+}
+
+// Runs conv `ci` of the plan (arena addressing) on the path the handle's precision selects.
+static int run_conv(pf_bgnet* net, const Arena& a, int ci, cudaStream_t st) {
+  const ConvDesc& c = net->convs[ci];
+  const bool head = ci == net->final_conv;
+  if (net->precision == 1 && !net->force_simt && net->plan.use_tc[ci])
+    return launch_conv_tc(net->plan.layers[ci], net->plan.maps_dev, net->plan.nblocks[ci], a.b, net->plan.smem[ci], st);
+  ConvLaunch L;
+  fill_conv_launch(net, a, c, &L);
+  if (head) L.cout_store = 16;
+  const bool sp = net->precision == 1;
+  return launch_conv_simt(L, c.ksize, c.stride, sp, sp && !head, st);
 }
 
 extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* depth_dev,
@@ -677,6 +900,11 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
   cudaStream_t st = (cudaStream_t)stream;
   Arena a;
   make_arena(net, workspace_dev, b, H, W, &a);
+  if (net->precision == 1 && !net->force_simt) {
+    int rc = ensure_tc_plan(net, a, workspace_dev);
+    if (rc) return rc;
+  }
+  const int split = a.split ? 1 : 0;
 
   const int nsteps = (int)net->steps.size();
   const bool prof = net->prof_iter < net->prof_cap;
@@ -690,7 +918,7 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         const ConvDesc& c = net->convs[s.conv];
         FirstParams p;
         p.labels = labels_dev; p.depth = depth_dev; p.mask = mask_dev; p.tab = net->first_tab_dev;
-        p.out = a.base + a.buf_off[c.out.buf];
+        p.out = a.ptr(c.out.buf, 0); p.out_lo = a.ptr_lo(c.out.buf, 0); p.split = split;
         p.b = b; p.t = net->num_inputs; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2;
         p.ncls = net->num_classes; p.use_depth = net->use_depth; p.mean = net->depth_mean; p.std = net->depth_std;
         const size_t smem = net->first_tab_floats * 4 + (size_t)p.t * F_IH * F_IW * 5 + 16;
@@ -706,10 +934,7 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         break;
       }
       case STEP_CONV: {
-        const ConvDesc& c = net->convs[s.conv];
-        ConvLaunch L;
-        fill_conv_launch(net, a, c, &L);
-        int rc = launch_conv_simt(L, c.ksize, c.stride, st);
+        int rc = run_conv(net, a, s.conv, st);
         if (rc) return rc;
         break;
       }
@@ -717,12 +942,13 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         const SegRef& in = s.in[0];
         const BufDesc& ib = net->bufs[in.buf];
         const BufDesc& ob = net->bufs[s.out.buf];
-        const int Ho = H >> ob.shift, Wo = W >> ob.shift;
-        const int c4 = in.cpad() / 4;
-        const size_t total = (size_t)b * Ho * Wo * c4;
-        avgpool2_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-            a.base + a.buf_off[in.buf] + in.coff, ib.cstride, align_up(a.img_floats[in.buf], 64),
-            a.base + a.buf_off[s.out.buf] + s.out.coff, ob.cstride, align_up(a.img_floats[s.out.buf], 64), b, Ho, Wo, c4);
+        PoolParams p;
+        p.in = a.ptr(in.buf, in.coff); p.in_lo = a.ptr_lo(in.buf, in.coff); p.in_cs = ib.cstride; p.in_img = a.img_elems[in.buf];
+        p.out = a.ptr(s.out.buf, s.out.coff); p.out_lo = a.ptr_lo(s.out.buf, s.out.coff); p.out_cs = ob.cstride;
+        p.out_img = a.img_elems[s.out.buf];
+        p.b = b; p.Ho = H >> ob.shift; p.Wo = W >> ob.shift; p.c4 = in.cpad() / 4; p.split = split;
+        const size_t total = (size_t)b * p.Ho * p.Wo * p.c4;
+        avgpool2_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
         PF_CHECK_CUDA(cudaGetLastError());
         break;
       }
@@ -732,19 +958,19 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         int ctot = 0;
         for (int k = 0; k < p.nseg; ++k) {
           const SegRef& r = s.in[k];
-          p.segs[k].base = a.base + a.buf_off[r.buf] + r.coff;
+          p.segs[k].base = a.ptr(r.buf, r.coff);
+          p.segs[k].base_lo = a.ptr_lo(r.buf, r.coff);
           p.segs[k].cstride = net->bufs[r.buf].cstride;
           p.segs[k].cpad = r.cpad();
-          p.in_img[k] = align_up(a.img_floats[r.buf], 64);
+          p.in_img[k] = a.img_elems[r.buf];
           ctot += r.cpad();
         }
-        // NOTE: the upsampled buffer is the contiguous concatenation of the PADDED input slices, so
-        // its consumer (conv1x1_up) must see the same padded channel positions -> handled below.
         const BufDesc& ib = net->bufs[s.in[0].buf];
         const BufDesc& ob = net->bufs[s.out.buf];
-        p.out = a.base + a.buf_off[s.out.buf]; p.out_cs = ob.cstride; p.out_img = align_up(a.img_floats[s.out.buf], 64);
+        p.out = a.ptr(s.out.buf, 0); p.out_lo = a.ptr_lo(s.out.buf, 0); p.out_cs = ob.cstride;
+        p.out_img = a.img_elems[s.out.buf];
         p.b = b; p.Hi = H >> ib.shift; p.Wi = W >> ib.shift; p.Ho = H >> ob.shift; p.Wo = W >> ob.shift;
-        p.c4_total = ctot / 4;
+        p.c4_total = ctot / 4; p.split = split;
         p.sh = p.Ho > 1 ? (float)(p.Hi - 1) / (float)(p.Ho - 1) : 0.f;
         p.sw = p.Wo > 1 ? (float)(p.Wi - 1) / (float)(p.Wo - 1) : 0.f;
         const size_t total = (size_t)b * p.Ho * p.Wo * p.c4_total;
@@ -753,14 +979,10 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         break;
       }
       case STEP_HEAD: {
-        const ConvDesc& c = net->convs[s.conv];
-        ConvLaunch L;
-        fill_conv_launch(net, a, c, &L);
-        L.cout_store = 16;
-        int rc = launch_conv_simt(L, 1, 1, st);
+        int rc = run_conv(net, a, s.conv, st);
         if (rc) return rc;
         const int h = H / 4, w = W / 4;
-        const float* q = a.base + a.buf_off[net->quarter_buf];
+        const float* q = reinterpret_cast<const float*>(a.ptr(net->quarter_buf, 0));
         if (out_quarter_dev) {
           const size_t total = (size_t)b * net->num_classes * h * w;
           nhwc16_to_nchw_kernel<<<grid_for(total, 256), 256, 0, st>>>(q, out_quarter_dev, b, net->num_classes, h, w);
@@ -833,6 +1055,8 @@ extern "C" int pf_upsample_argmax(const float* logits_nchw_dev, int b, int class
   return 0;
 }
 
+// One ConvLayer on an NCHW fp32 tensor through the SAME kernels the forward uses for it
+// (fp32 SIMT, split-bf16 SIMT for stride 2 / PF_TC_FORCE_SIMT, or the tcgen05 kernel).
 extern "C" int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_dev, int b, int H, int W,
                                    float* y_nchw_dev, void* stream) {
   PF_REQUIRE(net && x_nchw_dev && y_nchw_dev, PF_EINVAL, "pf_bgnet_debug_conv: null pointer");
@@ -840,43 +1064,80 @@ extern "C" int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_d
   const ConvDesc& c = net->convs[i];
   PF_REQUIRE(c.loaded, PF_ESTATE, "pf_bgnet_debug_conv: weights not loaded");
   cudaStream_t st = (cudaStream_t)stream;
-  // input: one contiguous NHWC buffer whose channel layout is the padded concatenation of the segs
+  const bool head = i == net->final_conv;
+  const bool split = net->precision == 1;
+  const bool split_out = split && !head;
   const int Ho = (H + c.stride - 1) / c.stride, Wo = (W + c.stride - 1) / c.stride;
-  const int cs_out = pad8(c.cout) < 16 && i == net->final_conv ? 16 : pad8(c.cout);
-  float *xin = nullptr, *yout = nullptr, *xpk = nullptr;
-  PF_CHECK_CUDA(cudaMalloc(&xin, (size_t)b * H * W * c.kpad * 4));
-  PF_CHECK_CUDA(cudaMalloc(&xpk, (size_t)b * H * W * c.cin * 4));
-  PF_CHECK_CUDA(cudaMalloc(&yout, (size_t)b * Ho * Wo * cs_out * 4));
-  PF_CHECK_CUDA(cudaMemsetAsync(xin, 0, (size_t)b * H * W * c.kpad * 4, st));
-  // NCHW -> dense NHWC (cin), then scatter each seg into its padded position
+  const int cs_out = head ? 16 : padc(c.cout);
+  const size_t in_elems = (size_t)b * H * W * c.kpad, out_elems = (size_t)b * Ho * Wo * cs_out;
+  const size_t esz_in = split ? 2 : 4, esz_out = split_out ? 2 : 4;
+  char *xin = nullptr, *xin_lo = nullptr, *yout = nullptr, *yout_lo = nullptr;
+  float* xpk = nullptr;
+  PF_CHECK_CUDA(cudaMalloc(&xin, in_elems * esz_in));
+  PF_CHECK_CUDA(cudaMalloc(&xin_lo, in_elems * 2));
+  PF_CHECK_CUDA(cudaMalloc(&xpk, (size_t)b * H * W * c.kpad * 4));
+  PF_CHECK_CUDA(cudaMalloc(&yout, out_elems * 4));
+  PF_CHECK_CUDA(cudaMalloc(&yout_lo, out_elems * 2));
+  // NCHW -> NCHW with each input slice moved to its padded channel position -> NHWC (kpad channels)
+  PF_CHECK_CUDA(cudaMemsetAsync(xpk, 0, (size_t)b * H * W * c.kpad * 4, st));
   {
-    const size_t total = (size_t)b * H * W * c.cin;
-    nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, st>>>(x_nchw_dev, xpk, b, c.cin, H, W, c.cin);
     int src = 0, dst = 0;
     for (auto& s : c.in) {
-      PF_CHECK_CUDA(cudaMemcpy2DAsync(xin + dst, (size_t)c.kpad * 4, xpk + src, (size_t)c.cin * 4, (size_t)s.c * 4,
-                                      (size_t)b * H * W, cudaMemcpyDeviceToDevice, st));
+      PF_CHECK_CUDA(cudaMemcpy2DAsync(xpk + (size_t)dst * H * W, (size_t)c.kpad * H * W * 4,
+                                      x_nchw_dev + (size_t)src * H * W, (size_t)c.cin * H * W * 4,
+                                      (size_t)s.c * H * W * 4, b, cudaMemcpyDeviceToDevice, st));
       src += s.c; dst += s.cpad();
     }
+    nchw_to_nhwc_kernel<<<grid_for(in_elems, 256), 256, 0, st>>>(xpk, xin, xin_lo, split ? 1 : 0, b, c.kpad, H, W, c.kpad);
+    PF_CHECK_CUDA(cudaGetLastError());
   }
-  ConvLaunch L;
-  L.nseg = (int)c.in.size();
-  int dst = 0;
-  for (int s = 0; s < L.nseg; ++s) {
-    L.segs[s].base = xin + dst; L.segs[s].cstride = c.kpad; L.segs[s].cpad = c.in[s].cpad();
-    L.in_img_stride[s] = (size_t)H * W * c.kpad;
-    dst += c.in[s].cpad();
+  int rc = 0;
+  const bool use_tc = split && !net->force_simt && c.stride == 1;
+  CUtensorMap* maps_dev = nullptr;
+  if (use_tc) {
+    TcIo io;
+    int dst = 0;
+    for (size_t s = 0; s < c.in.size(); ++s) {
+      io.in_hi[s] = xin + (size_t)dst * 2; io.in_lo[s] = xin_lo + (size_t)dst * 2;
+      io.in_cs[s] = c.kpad; io.in_img[s] = (size_t)H * W * c.kpad;
+      dst += c.in[s].cpad();
+    }
+    io.Hin = H; io.Win = W; io.Hout = Ho; io.Wout = Wo; io.b = b;
+    io.out_hi = head ? nullptr : yout; io.out_lo = head ? nullptr : yout_lo;
+    io.out_f32 = head ? reinterpret_cast<float*>(yout) : nullptr;
+    io.out_cs = cs_out; io.out_img = (size_t)Ho * Wo * cs_out;
+    std::vector<CUtensorMap> maps;
+    TcLayer L;
+    int nblocks; size_t smem;
+    rc = build_tc_layer(net, i, io, &maps, &L, &nblocks, &smem);
+    if (rc == 0) {
+      PF_CHECK_CUDA(cudaMalloc(&maps_dev, maps.size() * sizeof(CUtensorMap)));
+      PF_CHECK_CUDA(cudaMemcpyAsync(maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+      PF_CHECK_CUDA(cudaStreamSynchronize(st));
+      rc = launch_conv_tc(L, maps_dev, nblocks, b, smem, st);
+    }
+  } else {
+    ConvLaunch L;
+    L.nseg = (int)c.in.size();
+    int dst = 0;
+    for (int s = 0; s < L.nseg; ++s) {
+      L.segs[s].base = xin + (size_t)dst * esz_in; L.segs[s].base_lo = xin_lo + (size_t)dst * 2;
+      L.segs[s].cstride = c.kpad; L.segs[s].cpad = c.in[s].cpad();
+      L.in_img_stride[s] = (size_t)H * W * c.kpad;
+      dst += c.in[s].cpad();
+    }
+    L.b = b; L.Hin = H; L.Win = W; L.Hout = Ho; L.Wout = Wo;
+    L.out = yout; L.out_lo = yout_lo; L.out_cstride = cs_out; L.out_img_stride = (size_t)Ho * Wo * cs_out;
+    L.w = c.w_dev; L.bias = c.bias_dev; L.kpad = c.kpad; L.coutpad = c.coutpad; L.cout_store = cs_out; L.relu = c.relu ? 1 : 0;
+    rc = launch_conv_simt(L, c.ksize, c.stride, split, split_out, st);
   }
-  L.b = b; L.Hin = H; L.Win = W; L.Hout = Ho; L.Wout = Wo;
-  L.out = yout; L.out_cstride = cs_out; L.out_img_stride = (size_t)Ho * Wo * cs_out;
-  L.w = c.w_dev; L.bias = c.bias_dev; L.kpad = c.kpad; L.coutpad = c.coutpad; L.cout_store = cs_out; L.relu = c.relu ? 1 : 0;
-  int rc = launch_conv_simt(L, c.ksize, c.stride, st);
   if (rc == 0) {
     const size_t total = (size_t)b * c.cout * Ho * Wo;
-    nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, st>>>(yout, y_nchw_dev, b, c.cout, Ho, Wo, cs_out);
+    nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, st>>>(yout, yout_lo, split_out ? 1 : 0, y_nchw_dev, b, c.cout, Ho, Wo, cs_out);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("pf_bgnet_debug_conv: %s", cudaGetErrorString(e)); rc = (int)e; }
   }
-  cudaFree(xin); cudaFree(xpk); cudaFree(yout);
+  cudaFree(xin); cudaFree(xin_lo); cudaFree(xpk); cudaFree(yout); cudaFree(yout_lo);
+  if (maps_dev) cudaFree(maps_dev);
   return rc;
 }

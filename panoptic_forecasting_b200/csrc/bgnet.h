@@ -8,7 +8,7 @@
 namespace pf {
 
 constexpr int kMaxSegs = 10;     // conv1x1_up reads <=5 upsampled block-output slots + <=5 skip slots
-constexpr int kChanAlign = 8;    // every activation slot starts at, and is padded to, 8 channels
+constexpr int kChanAlign = 16;   // every activation slot starts at, and is padded to, 16 channels (one bf16 UMMA K atom)
 
 struct SegRef {                  // a channel slice of an NHWC activation buffer
   int buf = -1;
@@ -50,7 +50,8 @@ struct Step {
 
 // Device-side views --------------------------------------------------------------------------
 struct SegView {
-  const float* base;             // pixel (0,0) of image 0, channel coff
+  const void* base;              // pixel (0,0) of image 0, channel coff: fp32, or bf16 hi plane (split storage)
+  const void* base_lo;           // bf16 lo plane (split storage) or nullptr
   int cstride;
   int cpad;
 };
@@ -59,8 +60,9 @@ struct ConvLaunch {
   SegView segs[kMaxSegs];
   int nseg;
   int b, Hin, Win, Hout, Wout;
-  size_t in_img_stride[kMaxSegs];  // floats per image for each seg's buffer
-  float* out;                    // pixel (0,0) of image 0, channel out.coff
+  size_t in_img_stride[kMaxSegs];  // elements per image for each seg's buffer
+  void* out;                     // pixel (0,0) of image 0, channel out.coff (fp32, or bf16 hi plane)
+  void* out_lo;                  // bf16 lo plane (split storage) or nullptr
   int out_cstride;
   size_t out_img_stride;
   const float* w;
@@ -69,6 +71,7 @@ struct ConvLaunch {
   int relu;
 };
 
-int launch_conv_simt(const ConvLaunch& L, int ksize, int stride, cudaStream_t st);
+// split_in / split_out: activations stored as bf16 (hi, lo) planes with x = hi + lo (tensor-core path storage)
+int launch_conv_simt(const ConvLaunch& L, int ksize, int stride, bool split_in, bool split_out, cudaStream_t st);
 
 }  // namespace pf

@@ -8,7 +8,10 @@
 // channels (32 fp32 accumulators).  Per 8-channel chunk the CTA stages the input halo tile
 // ([8][rows][cols] transposed, row pitch padded to avoid bank conflicts) and the 9-tap weight
 // slab in shared memory; each thread reuses one row of halo values across the 3 horizontal taps.
+#include <cuda_bf16.h>
+
 #include "bgnet.h"
+#include "split_bf16.cuh"
 
 namespace pf {
 
@@ -22,7 +25,11 @@ struct HaloGeom {
   static constexpr int na = (PXT - 1) * STRIDE + KS;                  // halo values per thread-row
 };
 
-template <int KS, int STRIDE, int NT>
+__device__ __forceinline__ float4 load4(const SegView& sv, size_t off, bool split) {
+  return load4_any(sv.base, sv.base_lo, off, split);
+}
+
+template <int KS, int STRIDE, int NT, bool SPLIT_IN, bool SPLIT_OUT>
 __global__ void __launch_bounds__(16 * NT / 4) conv_simt_kernel(const ConvLaunch L) {
   using G = HaloGeom<KS, STRIDE>;
   constexpr int NTHREADS = 16 * NT / 4;
@@ -53,7 +60,7 @@ __global__ void __launch_bounds__(16 * NT / 4) conv_simt_kernel(const ConvLaunch
   int kbase = 0;
   for (int s = 0; s < L.nseg; ++s) {
     const SegView sv = L.segs[s];
-    const float* img_base = sv.base + (size_t)img * L.in_img_stride[s];
+    const size_t img_off = (size_t)img * L.in_img_stride[s];
     for (int c0 = 0; c0 < sv.cpad; c0 += KC) {
       // ---- stage A halo tile: each task = one halo pixel x 4 channels (float4)
       for (int task = tid; task < G::rows * G::cols * (KC / 4); task += NTHREADS) {
@@ -63,7 +70,7 @@ __global__ void __launch_bounds__(16 * NT / 4) conv_simt_kernel(const ConvLaunch
         const int iy = iy0 + hy, ix = ix0 + hx;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win)
-          v = __ldg(reinterpret_cast<const float4*>(img_base + ((size_t)iy * L.Win + ix) * sv.cstride + c0 + half * 4));
+          v = load4(sv, img_off + ((size_t)iy * L.Win + ix) * sv.cstride + c0 + half * 4, SPLIT_IN);
         const int o = hy * G::pitch + hx;
         As[half * 4 + 0][o] = v.x;
         As[half * 4 + 1][o] = v.y;
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(16 * NT / 4) conv_simt_kernel(const ConvLaunch
   const float4 bv = *reinterpret_cast<const float4*>(L.bias + n);
   const int oy = oy0 + py;
   if (oy >= L.Hout) return;
-  float* orow = L.out + (size_t)img * L.out_img_stride + (size_t)oy * L.Wout * L.out_cstride + n;
+  const size_t orow = (size_t)img * L.out_img_stride + (size_t)oy * L.Wout * L.out_cstride + n;
 #pragma unroll
   for (int i = 0; i < PXT; ++i) {
     const int ox = ox0 + px0 + i;
@@ -123,32 +130,48 @@ __global__ void __launch_bounds__(16 * NT / 4) conv_simt_kernel(const ConvLaunch
     if (L.relu) {
       r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
     }
-    *reinterpret_cast<float4*>(orow + (size_t)ox * L.out_cstride) = r;
+    const size_t o = orow + (size_t)ox * L.out_cstride;
+    if (!SPLIT_OUT) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(L.out) + o) = r;
+    } else {
+      uint2 h, l;
+      split_store4(r, &h, &l);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(L.out) + o) = h;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(L.out_lo) + o) = l;
+    }
   }
 }
 
-template <int KS, int STRIDE>
+template <int KS, int STRIDE, bool SI, bool SO>
 static int launch_nt(const ConvLaunch& L, cudaStream_t st) {
   const int tiles = cdiv(L.Hout, TH) * cdiv(L.Wout, TW);
   const int cs = L.cout_store;
   // NT = 16 for the narrowest layers, else whichever of 32 / 64 pads fewer columns (ties -> 64).
   if (cs <= 16) {
-    conv_simt_kernel<KS, STRIDE, 16><<<dim3(tiles, cdiv(cs, 16), L.b), 64, 0, st>>>(L);
+    conv_simt_kernel<KS, STRIDE, 16, SI, SO><<<dim3(tiles, cdiv(cs, 16), L.b), 64, 0, st>>>(L);
   } else if (cdiv(cs, 32) * 32 < cdiv(cs, 64) * 64) {
-    conv_simt_kernel<KS, STRIDE, 32><<<dim3(tiles, cdiv(cs, 32), L.b), 128, 0, st>>>(L);
+    conv_simt_kernel<KS, STRIDE, 32, SI, SO><<<dim3(tiles, cdiv(cs, 32), L.b), 128, 0, st>>>(L);
   } else {
-    conv_simt_kernel<KS, STRIDE, 64><<<dim3(tiles, cdiv(cs, 64), L.b), 256, 0, st>>>(L);
+    conv_simt_kernel<KS, STRIDE, 64, SI, SO><<<dim3(tiles, cdiv(cs, 64), L.b), 256, 0, st>>>(L);
   }
   PF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_conv_simt(const ConvLaunch& L, int ksize, int stride, cudaStream_t st) {
-  if (ksize == 3 && stride == 1) return launch_nt<3, 1>(L, st);
-  if (ksize == 3 && stride == 2) return launch_nt<3, 2>(L, st);
-  if (ksize == 1 && stride == 1) return launch_nt<1, 1>(L, st);
+template <bool SI, bool SO>
+static int launch_ks(const ConvLaunch& L, int ksize, int stride, cudaStream_t st) {
+  if (ksize == 3 && stride == 1) return launch_nt<3, 1, SI, SO>(L, st);
+  if (ksize == 3 && stride == 2) return launch_nt<3, 2, SI, SO>(L, st);
+  if (ksize == 1 && stride == 1) return launch_nt<1, 1, SI, SO>(L, st);
   set_error("launch_conv_simt: unsupported ksize=%d stride=%d", ksize, stride);
   return PF_EINVAL;
+}
+
+int launch_conv_simt(const ConvLaunch& L, int ksize, int stride, bool split_in, bool split_out, cudaStream_t st) {
+  if (!split_in && !split_out) return launch_ks<false, false>(L, ksize, stride, st);
+  if (split_in && split_out) return launch_ks<true, true>(L, ksize, stride, st);
+  if (split_in && !split_out) return launch_ks<true, false>(L, ksize, stride, st);
+  return launch_ks<false, true>(L, ksize, stride, st);
 }
 
 }  // namespace pf

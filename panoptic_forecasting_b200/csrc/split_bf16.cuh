@@ -1,0 +1,50 @@
+// Split-bf16 activation storage of the tensor-core path: x (fp32) is kept as two bf16 planes,
+// hi = bf16_rn(x) and lo = bf16_rn(x - hi), so that hi + lo carries ~16 mantissa bits and the
+// three tensor-core products (hi*Whi + lo*Whi + hi*Wlo) reproduce the fp32 convolution to ~3e-5.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace pf {
+
+__device__ __forceinline__ void split1(float x, unsigned* hi, unsigned* lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  *hi = (unsigned)__bfloat16_as_ushort(h);
+  *lo = (unsigned)__bfloat16_as_ushort(l);
+}
+
+__device__ __forceinline__ void split_store4(const float4& r, uint2* h, uint2* l) {
+  unsigned h0, h1, h2, h3, l0, l1, l2, l3;
+  split1(r.x, &h0, &l0); split1(r.y, &h1, &l1); split1(r.z, &h2, &l2); split1(r.w, &h3, &l3);
+  h->x = h0 | (h1 << 16); h->y = h2 | (h3 << 16);
+  l->x = l0 | (l1 << 16); l->y = l2 | (l3 << 16);
+}
+
+__device__ __forceinline__ float bf16lo(unsigned packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16hi(unsigned packed) { return __uint_as_float(packed & 0xFFFF0000u); }
+
+// 4 consecutive channels at element offset `off`: fp32 buffer, or (hi, lo) bf16 planes.
+__device__ __forceinline__ float4 load4_any(const void* base, const void* base_lo, size_t off, bool split) {
+  if (!split) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+  const uint2 l = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base_lo) + off));
+  float4 r;
+  r.x = bf16lo(h.x) + bf16lo(l.x);
+  r.y = bf16hi(h.x) + bf16hi(l.x);
+  r.z = bf16lo(h.y) + bf16lo(l.y);
+  r.w = bf16hi(h.y) + bf16hi(l.y);
+  return r;
+}
+__device__ __forceinline__ void store4_any(void* base, void* base_lo, size_t off, const float4& r, bool split) {
+  if (!split) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = r;
+  } else {
+    uint2 h, l;
+    split_store4(r, &h, &l);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = h;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base_lo) + off) = l;
+  }
+}
+
+}  // namespace pf

@@ -1,0 +1,71 @@
+"""GPU parity of the tensor-core (tcgen05, split-bf16 3-pass) Stage B path vs the oracle and vs
+the fp32 SIMT path.  Tolerances: north_star asks <= 1e-3 relative on logits; the split-bf16
+scheme is expected (oracle/precision study in DESIGN.md) to land near 3e-5, asserted <= 3e-4."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import bg_oracle
+from panoptic_forecasting_b200 import _lib, synthetic
+from test_bgnet_gpu import check_against, gpu_model
+
+pytestmark = pytest.mark.gpu
+
+
+def layer_sweep(pf_lib, bg_shapes, tol):
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=2)
+    m = gpu_model(sd, precision="tc")
+    m._upload(torch.device("cuda", torch.cuda.current_device()))
+    n = pf_lib.pf_bgnet_num_convs(m._net)
+    info = _lib.ConvInfo()
+    g = torch.Generator().manual_seed(0)
+    worst = 0.0
+    for i in range(1, n + 1):
+        assert pf_lib.pf_bgnet_conv_info(m._net, i, C.byref(info)) == 0
+        name = info.name.decode()
+        H, W = (24, 40) if info.stride == 1 else (24, 48)
+        x = torch.randn(2, info.cin, H, W, generator=g).relu()
+        if i < n:
+            ref = bg_oracle.conv_layer(sd, name, x, info.ksize, info.stride)
+        else:
+            ref = F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"])
+        y = torch.empty(ref.shape, device="cuda")
+        rc = pf_lib.pf_bgnet_debug_conv(m._net, i, x.cuda().data_ptr(), 2, H, W, y.data_ptr(), None)
+        assert rc == 0, (name, pf_lib.pf_last_error())
+        err = (y.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+        assert err <= tol, (i, name, info.cin, info.cout, info.ksize, err)
+        worst = max(worst, err)
+    return worst
+
+
+def test_split_storage_simt_kernels(pf_lib, bg_shapes, monkeypatch):
+    """Split-bf16 storage with every conv forced onto the SIMT kernels (isolates storage from UMMA)."""
+    monkeypatch.setenv("PF_TC_FORCE_SIMT", "1")
+    layer_sweep(pf_lib, bg_shapes, 1e-4)
+
+
+def test_every_conv_layer_tcgen05(pf_lib, bg_shapes, monkeypatch):
+    monkeypatch.delenv("PF_TC_FORCE_SIMT", raising=False)
+    worst = layer_sweep(pf_lib, bg_shapes, 1e-4)
+    print("worst per-layer relative error (tcgen05 split-bf16):", worst)
+
+
+@pytest.mark.parametrize("shape,final", [((1, 3, 64, 128), None), ((2, 3, 128, 192), (256, 384)), ((1, 3, 256, 512), None)])
+def test_whole_net_tcgen05(pf_lib, bg_shapes, shape, final):
+    b, t, h, w = shape
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=h)
+    pc = synthetic.make_pc_inputs(b, 3, h, w, "R", seed=h)
+    inp = {"seg": pc["seg"].long(), "depth": pc["depth"].clamp(0.1, 200), "depth_mask": pc["depth_mask"]}
+    q = bg_oracle.predict(sd, inp, final)["orig_size_logits"]
+    sd["model.finalConv.bias"] = sd["model.finalConv.bias"] - q.mean((0, 2, 3))
+    ref = bg_oracle.predict(sd, inp, final)
+    cu = {k: v.cuda() for k, v in inp.items()}
+    out = gpu_model(sd, final, precision="tc").predict(cu, {})
+    err, mism = check_against(out, ref, rel_tol=3e-4)
+    print("tcgen05 path: logits rel err %.2e, label mismatches %d of %d" % (err, mism, ref["seg"].numel()))
+    # against the fp32 SIMT path on the same device
+    out32 = gpu_model(sd, final, precision="fp32").predict(cu, {})
+    scale = out32["logits"].abs().max().item()
+    assert (out["logits"] - out32["logits"]).abs().max().item() <= 3e-4 * scale
