@@ -308,7 +308,7 @@ int launch_conv_tc(const TcLayer& L, const CUtensorMap* maps_dev, int nblocks, i
                    cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    PF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr = true;
   }
   dim3 grid(L.tiles_x * L.tiles_y, nblocks, batch);

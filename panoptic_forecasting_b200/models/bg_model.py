@@ -60,7 +60,7 @@ class BGModel(BaseModel):
             self.depth_std = nn.Parameter(torch.as_tensor(std, dtype=torch.float32).reshape(1), requires_grad=False)
         # B200-path options (absent keys keep the reference's outputs)
         b200 = params['model'].get('b200', {}) or {}
-        self.precision = {'fp32': 0, 'tc': 1}[b200.get('precision', 'fp32')]
+        self.precision = {'fp32': 0, 'tc': 1}[b200.get('precision', 'tc')]
         self.return_logits = b200.get('return_logits', True)
         self.seg_dtype = b200.get('seg_dtype', 'int64')
 

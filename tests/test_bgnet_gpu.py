@@ -24,6 +24,7 @@ REL_TOL = 1e-3
 
 def gpu_model(sd, final=None, **b200):
     fh, fw = final if final is not None else (None, None)
+    b200.setdefault("precision", "fp32")
     m = build_model(dict(bg_params(fh, fw, **b200), no_gpu=False)).eval()
     m.load_state_dict(sd)
     return m

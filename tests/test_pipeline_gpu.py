@@ -42,7 +42,7 @@ def test_composite_matches_composite_oracle(pf_lib, bg_shapes, b, h, w):
     sd["model.finalConv.bias"] = sd["model.finalConv.bias"] - q.mean((0, 2, 3))
     ref = bg_oracle.predict(sd, bg_in, None)
 
-    bg = build_model(dict(bg_params(), no_gpu=False)).eval()
+    bg = build_model(dict(bg_params(precision="fp32"), no_gpu=False)).eval()
     bg.load_state_dict(sd)
     pipe = BGForecastPipeline(bg)
     cu = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in npin.items()}
