@@ -222,7 +222,7 @@ def main():
         if store is not None:
             store.copy_(out["seg"])
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # runs through warm-up + both timed regions
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get('PF_NO_SAMPLER')) else None   # runs through warm-up + both timed regions
     # ---- warm-up
     for i in range(args.warmup):
         step_resident(i)
@@ -270,6 +270,8 @@ def main():
         else:
             other_ms += ms_steps[k]
     warp_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in ev_a)
+    if os.environ.get('PF_BENCH_DEBUG'):
+        print('warp ms per step:', ['%.2f' % a.elapsed_time(b_) for a, b_ in ev_a], file=sys.stderr)
     peaks = load_peaks()
     # dominant kernel family: the ConvLayer kernels (68 launches/step; first conv + head timed separately)
     conv_tflops = STAGE_B_FLOP_PER_FRAME * B / (max(conv_ms + first_ms, 1e-9) * 1e-3) / 1e12

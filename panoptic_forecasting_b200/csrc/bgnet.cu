@@ -80,12 +80,14 @@ struct pf_bgnet {
   struct TcPlan {
     const void* ws = nullptr; int b = 0, H = 0, W = 0;
     CUtensorMap* maps_dev = nullptr;
-    std::vector<TcLayer> layers;             // indexed by conv
+    std::vector<TcLayer> layers;             // indexed by conv (per-tap kernel: 1x1 convs, fallbacks)
+    std::vector<HaloLayer> halos;            // indexed by conv (halo kernel: 3x3 stride-1 convs)
     std::vector<int> nblocks;
     std::vector<size_t> smem;
-    std::vector<char> use_tc;
+    std::vector<char> use_tc;                // 0 SIMT, 1 per-tap tcgen05, 2 halo tcgen05
   } plan;
   bool force_simt = false;                   // PF_TC_FORCE_SIMT=1: run every conv on the SIMT kernels (A/B checks)
+  bool no_halo = false;                      // PF_TC_NO_HALO=1: 3x3 convs on the per-tap tcgen05 kernel
   // optional per-step CUDA-event profiling (bench.py roofline): ring of [iters][steps+1] events
   std::vector<cudaEvent_t> prof_ev;
   int prof_cap = 0, prof_iter = 0;
@@ -607,10 +609,7 @@ static int upload_conv_tc(pf_bgnet* net, int i) {
   }
   const int taps = c.ksize * c.ksize;
   const int ktot = taps * c.kpad;
-  int ntile, nblocks, stages, cols;
-  size_t smem;
-  tc_pick_tiling(c.coutpad, &ntile, &nblocks, &stages, &cols, &smem);
-  const int nrows = ntile * nblocks;
+  const int nrows = c.coutpad;      // rows beyond it are TMA out-of-bounds zero fill
   std::vector<unsigned short> w((size_t)2 * nrows * ktot, 0);
   int kp = 0, kb = 0;
   for (auto& s : c.in) {
@@ -667,7 +666,7 @@ static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUte
   }
   const int ktot = taps * c.kpad;
   int ntile, nb, stages, cols;
-  tc_pick_tiling(c.coutpad, &ntile, &nb, &stages, &cols, smem);
+  tc_pick_tiling(c.coutpad, cdiv(io.Wout, 16) * cdiv(io.Hout, 8) * io.b, &ntile, &nb, &stages, &cols, smem);
   *nblocks = nb;
   const int nrows = net->wtc_rows[i];
   L->w_map = (int)maps->size();
@@ -694,12 +693,76 @@ static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUte
   return 0;
 }
 
+// Halo-kernel plan of a 3x3 / stride-1 conv.  Returns 1 when the layer does not fit (caller falls
+// back to the per-tap kernel), 0 on success, <0 / cudaError on failure.
+static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUtensorMap>* maps, HaloLayer* L,
+                            int* nblocks, size_t* smem) {
+  const ConvDesc& c = net->convs[i];
+  if (c.ksize != 3 || c.stride != 1 || io.out_f32) return 1;
+  memset(L, 0, sizeof(*L));
+  int ntile, nb, stages, cols;
+  size_t dummy;
+  tc_pick_tiling(c.coutpad, cdiv(io.Wout, 8) * cdiv(io.Hout, 16) * io.b, &ntile, &nb, &stages, &cols, &dummy);
+  L->nseg = (int)c.in.size();
+  L->ntile = ntile;
+  int kb = 0;
+  bool used[3] = {false, false, false};
+  for (int s = 0; s < L->nseg; ++s) {
+    const int cp = c.in[s].cpad();
+    L->seg_cpad[s] = cp;
+    L->seg_w[s] = halo_chunk_width(cp);
+    used[L->seg_w[s] >> 5] = true;
+    L->seg_koff[s] = kb;
+    kb += 9 * cp;
+  }
+  if (!halo_plan_smem(L, smem)) return 1;
+  for (int s = 0; s < L->nseg; ++s) {
+    L->seg_map[s] = (int)maps->size();
+    CUtensorMap m;
+    int rc = halo_encode_act_map(&m, io.in_hi[s], L->seg_cpad[s], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[s]);
+    if (rc) return rc;
+    maps->push_back(m);
+    rc = halo_encode_act_map(&m, io.in_lo[s], L->seg_cpad[s], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[s]);
+    if (rc) return rc;
+    maps->push_back(m);
+  }
+  const int ktot = 9 * c.kpad;
+  const int nrows = net->wtc_rows[i];
+  for (int k = 0; k < 3; ++k) {
+    L->w_map[k] = -1;
+    if (!used[k]) continue;
+    const int w = 16 << k;
+    L->w_map[k] = (int)maps->size();
+    CUtensorMap m;
+    int rc = halo_encode_weight_map(&m, net->wtc_dev[i], ktot, nrows, ntile, w);
+    if (rc) return rc;
+    maps->push_back(m);
+    rc = halo_encode_weight_map(&m, net->wtc_dev[i] + (size_t)nrows * ktot, ktot, nrows, ntile, w);
+    if (rc) return rc;
+    maps->push_back(m);
+  }
+  *nblocks = nb;
+  L->Hout = io.Hout; L->Wout = io.Wout; L->batch = io.b;
+  L->tiles_x = cdiv(io.Wout, 8); L->tiles_y = cdiv(io.Hout, 16);
+  int tcols = 32;
+  while (tcols < 4 * ntile) tcols <<= 1;
+  L->tmem_cols = tcols;
+  L->cout_store = padc(c.cout);
+  L->relu = c.relu ? 1 : 0;
+  L->out_hi = reinterpret_cast<__nv_bfloat16*>(io.out_hi);
+  L->out_lo = reinterpret_cast<__nv_bfloat16*>(io.out_lo);
+  L->out_cs = io.out_cs; L->out_img_stride = io.out_img;
+  L->bias = c.bias_dev;
+  return 0;
+}
+
 static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
   auto& P = net->plan;
   if (P.ws == ws && P.b == a.b && P.H == a.H && P.W == a.W && P.maps_dev) return 0;
   std::vector<CUtensorMap> maps;
   const size_t nc = net->convs.size();
   P.layers.assign(nc, TcLayer());
+  P.halos.assign(nc, HaloLayer());
   P.nblocks.assign(nc, 0);
   P.smem.assign(nc, 0);
   P.use_tc.assign(nc, 0);
@@ -720,7 +783,10 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
     io.out_lo = head ? nullptr : a.ptr_lo(c.out.buf, c.out.coff);
     io.out_f32 = head ? reinterpret_cast<float*>(a.ptr(c.out.buf, c.out.coff)) : nullptr;
     io.out_cs = ob.cstride; io.out_img = a.img_elems[c.out.buf];
-    int rc = build_tc_layer(net, (int)i, io, &maps, &P.layers[i], &P.nblocks[i], &P.smem[i]);
+    int rc = net->no_halo ? 1 : build_halo_layer(net, (int)i, io, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i]);
+    if (rc == 0) { P.use_tc[i] = 2; continue; }
+    if (rc != 1) return rc;
+    rc = build_tc_layer(net, (int)i, io, &maps, &P.layers[i], &P.nblocks[i], &P.smem[i]);
     if (rc) return rc;
     P.use_tc[i] = 1;
   }
@@ -748,6 +814,8 @@ extern "C" int pf_bgnet_create(pf_bgnet_t** out, int num_classes, int num_inputs
   net->precision = precision;
   const char* fs = getenv("PF_TC_FORCE_SIMT");
   net->force_simt = fs && fs[0] == '1';
+  const char* nh = getenv("PF_TC_NO_HALO");
+  net->no_halo = nh && nh[0] == '1';
   build_topology(net);
   *out = net;
   return 0;
@@ -876,7 +944,9 @@ extern "C" int pf_bgnet_launches_per_forward(const pf_bgnet_t* net) {
 static int run_conv(pf_bgnet* net, const Arena& a, int ci, cudaStream_t st) {
   const ConvDesc& c = net->convs[ci];
   const bool head = ci == net->final_conv;
-  if (net->precision == 1 && !net->force_simt && net->plan.use_tc[ci])
+  if (net->precision == 1 && !net->force_simt && net->plan.use_tc[ci] == 2)
+    return launch_conv_halo(net->plan.halos[ci], net->plan.maps_dev, net->plan.nblocks[ci], net->plan.smem[ci], st);
+  if (net->precision == 1 && !net->force_simt && net->plan.use_tc[ci] == 1)
     return launch_conv_tc(net->plan.layers[ci], net->plan.maps_dev, net->plan.nblocks[ci], a.b, net->plan.smem[ci], st);
   ConvLaunch L;
   fill_conv_launch(net, a, c, &L);
@@ -1108,13 +1178,34 @@ extern "C" int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_d
     io.out_cs = cs_out; io.out_img = (size_t)Ho * Wo * cs_out;
     std::vector<CUtensorMap> maps;
     TcLayer L;
+    HaloLayer HL;
     int nblocks; size_t smem;
-    rc = build_tc_layer(net, i, io, &maps, &L, &nblocks, &smem);
+    int kind = 2;
+    rc = net->no_halo ? 1 : build_halo_layer(net, i, io, &maps, &HL, &nblocks, &smem);
+    if (rc == 1) { kind = 1; rc = build_tc_layer(net, i, io, &maps, &L, &nblocks, &smem); }
     if (rc == 0) {
       PF_CHECK_CUDA(cudaMalloc(&maps_dev, maps.size() * sizeof(CUtensorMap)));
       PF_CHECK_CUDA(cudaMemcpyAsync(maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
       PF_CHECK_CUDA(cudaStreamSynchronize(st));
-      rc = launch_conv_tc(L, maps_dev, nblocks, b, smem, st);
+      long long* ts_dev = nullptr;
+      if (kind == 2 && getenv("PF_HALO_TS")) {
+        cudaMalloc(&ts_dev, 16 * sizeof(long long));
+        cudaMemset(ts_dev, 0, 16 * sizeof(long long));
+        HL.dbg_ts = ts_dev;
+        launch_conv_halo(HL, maps_dev, nblocks, smem, st);      // warm (weights / descriptors in L2)
+      }
+      rc = kind == 2 ? launch_conv_halo(HL, maps_dev, nblocks, smem, st) : launch_conv_tc(L, maps_dev, nblocks, b, smem, st);
+      if (ts_dev) {
+        long long ts[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(ts, ts_dev, sizeof(ts), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[halo ts] %s tiles=%d nblk=%d res=%d SA=%d SB=%d ntile=%d: setup %lld, w-ready %lld, first-A %lld, "
+                "tile0 mma-issued %lld, tile0 acc-ready %lld, tile0 epi-done %lld, all-mma-issued %lld, end %lld (cycles)\n",
+                c.name.c_str(), HL.tiles_x * HL.tiles_y * HL.batch, nblocks, HL.resident, HL.stages_a, HL.stages_b, HL.ntile,
+                ts[1] - ts[0], ts[2] - ts[0], ts[3] - ts[0], ts[4] - ts[0], ts[5] - ts[0], ts[6] - ts[0], ts[7] - ts[0],
+                ts[8] - ts[0]);
+        cudaFree(ts_dev);
+      }
     }
   } else {
     ConvLaunch L;

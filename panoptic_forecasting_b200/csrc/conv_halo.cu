@@ -1,0 +1,380 @@
+// Persistent halo-tile tcgen05 kernel for the 3x3 / stride-1 ConvLayers (hardnet.py:16-25; 56 of
+// the 70 convs).
+//
+// A CTA loops over 16-row x 8-column blocks of output pixels.  Per input-channel chunk (16, 32 or
+// 64 channels of one channel slice) ONE TMA box of 18 x 10 input pixels is staged per bf16 plane
+// and all nine filter taps read it through shifted UMMA descriptors: the 8 pixels of an
+// accumulator row group are consecutive swizzled rows of the box, row groups are 10 rows apart
+// (SBO = 10 * row pitch), and tap (dy,dx) moves the descriptor start by (dy*10+dx) rows.  (The
+// tensor core applies the 32/64/128-byte swizzle to absolute shared-memory address bits, so a
+// shifted start needs no re-layout -- verified on B200 against the fp32 kernels.)  Versus one box
+// per tap this cuts L2->SMEM activation traffic ~6x; image borders are TMA out-of-bounds zero
+// fill == the conv's zero padding.
+// Weights (split bf16, K-major) are either RESIDENT in shared memory for the whole kernel (the
+// high-resolution layers, where a CTA visits many tiles) or STREAMED per (chunk, tap) through a
+// second mbarrier ring.  The fp32 accumulator is double-buffered in TMEM so the epilogue of tile
+// i overlaps the MMAs of tile i+1.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "bgnet.h"
+#include "conv_tc.h"
+#include "split_bf16.cuh"
+#include "tc_common.cuh"
+
+namespace pf {
+
+using namespace tc;
+
+namespace {
+constexpr int kHX = 10, kHY = 18;               // halo box: 18 rows x 10 columns of input pixels
+constexpr int kMaxA = 4, kMaxB = 8;
+
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ uint32_t layout_of(int w) { return w == 64 ? 2u : (w == 32 ? 4u : 6u); }
+__device__ __forceinline__ uint32_t align1k(uint32_t x) { return (x + 1023u) & ~1023u; }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxB + 5];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const bool dbg = L.dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (dbg && threadIdx.x == 0) L.dbg_ts[0] = clock64();
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int ntile = L.ntile;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_a = [&](int s) { return bar0 + 8u * s; };
+  auto empty_a = [&](int s) { return bar0 + 8u * (kMaxA + s); };
+  auto full_b = [&](int s) { return bar0 + 8u * (2 * kMaxA + s); };
+  auto empty_b = [&](int s) { return bar0 + 8u * (2 * kMaxA + kMaxB + s); };
+  const uint32_t wbar = bar0 + 8u * (2 * kMaxA + 2 * kMaxB);
+  auto tmem_full = [&](int a) { return bar0 + 8u * (2 * kMaxA + 2 * kMaxB + 1 + a); };
+  auto tmem_empty = [&](int a) { return bar0 + 8u * (2 * kMaxA + 2 * kMaxB + 3 + a); };
+
+  const int SA = L.stages_a, SB = L.stages_b;
+  const uint32_t a_tile = L.a_tile_bytes;          // one plane of one A stage (1024-aligned)
+  const uint32_t b_tile = L.b_tile_bytes;          // one tap of the widest chunk: [hi rows ; lo rows], 1024-aligned
+  const uint32_t w_region = L.resident ? L.w_bytes_total : 0u;
+  const uint32_t a_base = smem_base + w_region;
+  const uint32_t b_base = a_base + SA * 2 * a_tile;
+  const int n0 = blockIdx.y * ntile;
+  const int tiles_per_img = L.tiles_x * L.tiles_y;
+  const int total_tiles = tiles_per_img * L.batch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    mbar_init(wbar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"((uint32_t)L.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_smem;
+  if (dbg && threadIdx.x == 0) L.dbg_ts[1] = clock64();
+
+  if (warp == 0) {
+    // ===== TMA producer (warp-uniform loops, one elected lane issues) =====
+    const uint32_t el = elect_one();
+    {
+      if (L.resident) {
+        mbar_expect_tx_p(wbar, L.w_tx_total, el);
+        uint32_t off = 0;
+        for (int s = 0; s < L.nseg; ++s) {
+          const int cpad = L.seg_cpad[s], w = L.seg_w[s];
+          const CUtensorMap* wm = maps + L.w_map[w >> 5];          // 16 -> 0, 32 -> 1, 64 -> 2
+          const uint32_t bt = (uint32_t)ntile * 2u * w;            // hi rows, lo rows directly behind them
+          for (int c0 = 0; c0 < cpad; c0 += w)
+            for (int tap = 0; tap < 9; ++tap) {
+              const int koff = L.seg_koff[s] + tap * cpad + c0;
+              tma_load_2d_p(smem_base + off, wm, wbar, koff, n0, el);
+              tma_load_2d_p(smem_base + off + bt, wm + 1, wbar, koff, n0, el);
+              off += align1k(2 * bt);
+            }
+        }
+      }
+      int ia = 0, ib = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int img = t / tiles_per_img;
+        const int r = t - img * tiles_per_img;
+        const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
+        const int y0 = ty * 16, x0 = tx * 8;
+        for (int s = 0; s < L.nseg; ++s) {
+          const int cpad = L.seg_cpad[s], w = L.seg_w[s];
+          const CUtensorMap* am = maps + L.seg_map[s];
+          const CUtensorMap* wm = maps + L.w_map[w >> 5];
+          const uint32_t a_tx = (uint32_t)kHX * kHY * 2u * w;
+          const uint32_t b_tx = (uint32_t)ntile * 2u * w;
+          for (int c0 = 0; c0 < cpad; c0 += w, ++ia) {
+            const int st = ia % SA;
+            mbar_wait(empty_a(st), ((ia / SA) & 1) ^ 1);
+            const uint32_t sa = a_base + st * 2 * a_tile;
+            mbar_expect_tx_p(full_a(st), 2 * a_tx, el);
+            tma_load_4d_p(sa, am, full_a(st), c0, x0 - 1, y0 - 1, img, el);
+            tma_load_4d_p(sa + a_tile, am + 1, full_a(st), c0, x0 - 1, y0 - 1, img, el);
+            if (!L.resident) {
+              for (int tap = 0; tap < 9; ++tap, ++ib) {
+                const int sb = ib % SB;
+                mbar_wait(empty_b(sb), ((ib / SB) & 1) ^ 1);
+                const uint32_t sbp = b_base + sb * b_tile;
+                mbar_expect_tx_p(full_b(sb), 2 * b_tx, el);
+                const int koff = L.seg_koff[s] + tap * cpad + c0;
+                tma_load_2d_p(sbp, wm, full_b(sb), koff, n0, el);
+                tma_load_2d_p(sbp + b_tx, wm + 1, full_b(sb), koff, n0, el);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform loops, one elected lane issues) =====
+    const uint32_t el = elect_one();
+    {
+      // kind::f16, bf16 x bf16 -> fp32, M = 128.  Two MMAs per 16-channel K atom:
+      //   D[:, 0:2n] += A_hi * [W_hi ; W_lo]^T   (N = 2n: the hi and lo weight rows are adjacent in smem)
+      //   D[:, 0:n]  += A_lo * W_hi^T            (N = n)
+      // the epilogue adds the two column halves.  A (4 KB per MMA) is the shared-memory-bandwidth
+      // bound of small-N layers, so reading A_hi once instead of twice is a 1.5x saving.
+      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+      const uint32_t idesc1 = idesc_base | ((uint32_t)(ntile >> 3) << 17);
+      const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * ntile) >> 3) << 17);
+      if (L.resident) mbar_wait(wbar, 0);
+      if (dbg && el) L.dbg_ts[2] = clock64();
+      int ia = 0, ib = 0, tc_ = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
+        const int acc = tc_ & 1;
+        mbar_wait(tmem_empty(acc), ((tc_ >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_d + (uint32_t)(acc * 2 * ntile);
+        uint32_t woff = 0;
+        bool first = true;
+        for (int s = 0; s < L.nseg; ++s) {
+          const int cpad = L.seg_cpad[s], w = L.seg_w[s];
+          const uint32_t rp = 2u * w, lay = layout_of(w);
+          const uint32_t bt = (uint32_t)ntile * rp;
+          for (int c0 = 0; c0 < cpad; c0 += w, ++ia) {
+            const int st = ia % SA;
+            mbar_wait(full_a(st), (ia / SA) & 1);
+            if (dbg && el && ia == 0) L.dbg_ts[3] = clock64();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = a_base + st * 2 * a_tile;
+            const int nk = min(w, cpad - c0) >> 4;
+            // descriptors are linear in the start address: build the chunk's base descriptors once,
+            // then every (tap, k-atom) is one 64-bit add (the MMA issuer is a single thread).
+            const uint64_t a_hi0 = desc_kmajor(sa, kHX * rp, lay);
+            const uint64_t a_lo0 = desc_kmajor(sa + a_tile, kHX * rp, lay);
+            const uint32_t tap_step = rp >> 4;                   // one pixel row, in 16-byte units
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              const uint64_t shift = (uint64_t)((dy * kHX + dx) * tap_step);
+              uint32_t sb_hi;
+              int sbi = 0;
+              if (L.resident) {
+                sb_hi = smem_base + woff;
+                woff += align1k(2 * bt);
+              } else {
+                sbi = ib % SB;
+                mbar_wait(full_b(sbi), (ib / SB) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                sb_hi = b_base + sbi * b_tile;
+                ++ib;
+              }
+              const uint64_t b0 = desc_kmajor(sb_hi, 8 * rp, lay);
+#pragma unroll 4
+              for (int ka = 0; ka < nk; ++ka) {
+                const uint64_t ko = (uint64_t)(ka * 2);          // 32 bytes per k-atom
+                umma_bf16_p(d, a_hi0 + shift + ko, b0 + ko, idesc2, first ? 0u : 1u, el);
+                first = false;
+                umma_bf16_p(d, a_lo0 + shift + ko, b0 + ko, idesc1, 1u, el);
+              }
+              if (!L.resident) umma_commit_p(empty_b(sbi), el);
+            }
+            umma_commit_p(empty_a(st), el);
+          }
+        }
+        umma_commit_p(tmem_full(acc), el);
+        if (dbg && el && tc_ == 0) L.dbg_ts[4] = clock64();
+      }
+      if (dbg && el) L.dbg_ts[7] = clock64();
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int tc_ = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
+      const int acc = tc_ & 1;
+      const int img = t / tiles_per_img;
+      const int r = t - img * tiles_per_img;
+      const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
+      const int oy = ty * 16 + (m >> 3), ox = tx * 8 + (m & 7);
+      const bool inside = (oy < L.Hout) && (ox < L.Wout);
+      mbar_wait(tmem_full(acc), (tc_ >> 1) & 1);
+      if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[5] = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const size_t pix = (size_t)img * L.out_img_stride + ((size_t)oy * L.Wout + ox) * L.out_cs;
+      for (int c = 0; c < ntile; c += 16) {
+        const int n = n0 + c;
+        if (n >= L.cout_store) break;
+        float v[16], v2[16];
+        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * ntile + c), v);
+        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * ntile + ntile + c), v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = (v[i] + v2[i]) + __ldg(L.bias + n + i);
+          if (L.relu) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (!inside) continue;
+        uint4 h[2], l[2];
+        uint2 th, tl;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          split_store4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), &th, &tl);
+          reinterpret_cast<uint2*>(h)[i] = th;
+          reinterpret_cast<uint2*>(l)[i] = tl;
+        }
+        uint4* oh = reinterpret_cast<uint4*>(L.out_hi + pix + n);
+        uint4* ol = reinterpret_cast<uint4*>(L.out_lo + pix + n);
+        oh[0] = h[0]; oh[1] = h[1];
+        ol[0] = l[0]; ol[1] = l[1];
+      }
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty(acc));
+      if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[6] = clock64();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)L.tmem_cols));
+  }
+  if (dbg && threadIdx.x == 0) L.dbg_ts[8] = clock64();
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+static CUtensorMapSwizzle swizzle_of(int w) {
+  return w == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (w == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode2() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int halo_encode_act_map(CUtensorMap* out, const void* base, int c, int cstride, int W, int H, int N,
+                        size_t img_stride_elems, int w) {
+  EncodeTiledFn enc = get_encode2();
+  PF_REQUIRE(enc, PF_ESTATE, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)cstride * 2, (cuuint64_t)W * cstride * 2, (cuuint64_t)img_stride_elems * 2};
+  cuuint32_t box[4] = {(cuuint32_t)w, (cuuint32_t)kHX, (cuuint32_t)kHY, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(w), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PF_REQUIRE(r == CUDA_SUCCESS, PF_EINVAL, "cuTensorMapEncodeTiled(halo activation c=%d w=%d) failed: %d", c, w, (int)r);
+  return 0;
+}
+
+int halo_encode_weight_map(CUtensorMap* out, const void* base, int ktot, int nrows, int ntile, int w) {
+  EncodeTiledFn enc = get_encode2();
+  PF_REQUIRE(enc, PF_ESTATE, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)nrows};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)w, (cuuint32_t)ntile};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(w), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PF_REQUIRE(r == CUDA_SUCCESS, PF_EINVAL, "cuTensorMapEncodeTiled(halo weights k=%d w=%d) failed: %d", ktot, w, (int)r);
+  return 0;
+}
+
+int halo_chunk_width(int cpad) { return cpad >= 64 ? 64 : (cpad >= 32 ? 32 : 16); }
+
+// Fills the shared-memory plan of a layer; returns false when it cannot run on this kernel.
+bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
+  const size_t budget = 218 * 1024;
+  int wmax = 16;
+  size_t w_total = 0, w_tx = 0;
+  for (int s = 0; s < L->nseg; ++s) {
+    const int w = L->seg_w[s];
+    if (w > wmax) wmax = w;
+    const int nchunks = (L->seg_cpad[s] + w - 1) / w;
+    const size_t bt = align_up((size_t)2 * L->ntile * 2 * w, 1024);   // [hi rows ; lo rows] of one tap
+    w_total += (size_t)nchunks * 9 * bt;
+    w_tx += (size_t)nchunks * 9 * 2 * (size_t)L->ntile * 2 * w;
+  }
+  const size_t a_tile = align_up((size_t)kHX * kHY * 2 * wmax, 1024);
+  const size_t b_tile = align_up((size_t)2 * L->ntile * 2 * wmax, 1024);
+  L->a_tile_bytes = (uint32_t)a_tile;
+  L->b_tile_bytes = (uint32_t)b_tile;
+  if (w_total + 2 * (2 * a_tile) <= budget) {
+    L->resident = 1;
+    L->w_bytes_total = (uint32_t)w_total;
+    L->w_tx_total = (uint32_t)w_tx;
+    int sa = (int)((budget - w_total) / (2 * a_tile));
+    L->stages_a = sa > kMaxA ? kMaxA : sa;
+    L->stages_b = 1;
+    *smem_bytes = w_total + (size_t)L->stages_a * 2 * a_tile + 1024;
+    return true;
+  }
+  L->resident = 0;
+  L->w_bytes_total = 0;
+  L->w_tx_total = 0;
+  L->stages_a = 2;
+  const size_t rest = budget - 2 * (2 * a_tile);
+  int sb = (int)(rest / b_tile);
+  if (sb < 2) return false;
+  L->stages_b = sb > kMaxB ? kMaxB : sb;
+  *smem_bytes = (size_t)L->stages_a * 2 * a_tile + (size_t)L->stages_b * b_tile + 1024;
+  return true;
+}
+
+int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblocks, size_t smem_bytes, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    attr = true;
+  }
+  const int total_tiles = L.tiles_x * L.tiles_y * L.batch;
+  int gx = kNumSMs / nblocks;
+  if (gx < 1) gx = 1;
+  if (gx > total_tiles) gx = total_tiles;
+  conv_halo_kernel<<<dim3(gx, nblocks), kThreads, smem_bytes, st>>>(L, maps_dev);
+  PF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace pf

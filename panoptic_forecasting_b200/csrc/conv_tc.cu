@@ -19,94 +19,18 @@
 #include "bgnet.h"
 #include "conv_tc.h"
 #include "split_bf16.cuh"
+#include "tc_common.cuh"
 
 namespace pf {
 
-namespace {
-
-constexpr int kThreads = 192;
-constexpr int kTileH = 8, kTileW = 16;
-constexpr int kBlockK = 64;                       // channels per stage (128 bytes of bf16 = one swizzle row)
-constexpr int kATileBytes = 128 * kBlockK * 2;    // 16 KB per plane
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a trapped launch (reported error), never a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 22)) __trap();
-  }
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory operand descriptor (8-row groups 1024 B apart).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-}  // namespace
+using namespace tc;
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcLayer L, const CUtensorMap* __restrict__ maps) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kTcMaxStages + 1];
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int ntile = L.ntile;
   const uint32_t b_bytes = (uint32_t)ntile * kBlockK * 2;
@@ -140,8 +64,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcLayer L, c
   const uint32_t tmem_d = tmem_base_smem;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (warp-uniform loops, one elected lane issues) =====
+    const uint32_t el = elect_one();
+    {
       int it = 0;
       for (int s = 0; s < L.nseg; ++s) {
         const int cpad = L.seg_cpad[s];
@@ -152,21 +77,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcLayer L, c
             const int st = it % S;
             mbar_wait(empty_bar(st), ((it / S) & 1) ^ 1);
             const uint32_t sa = smem_base + st * stage_bytes;
-            mbar_expect_tx(full_bar(st), stage_bytes);
-            tma_load_4d(sa, mhi, full_bar(st), c0, x0 + dx - pad, y0 + dy - pad, img);
-            tma_load_4d(sa + kATileBytes, mhi + 1, full_bar(st), c0, x0 + dx - pad, y0 + dy - pad, img);
+            mbar_expect_tx_p(full_bar(st), stage_bytes, el);
+            tma_load_4d_p(sa, mhi, full_bar(st), c0, x0 + dx - pad, y0 + dy - pad, img, el);
+            tma_load_4d_p(sa + kATileBytes, mhi + 1, full_bar(st), c0, x0 + dx - pad, y0 + dy - pad, img, el);
             const int koff = L.seg_koff[s] + tap * cpad + c0;
-            tma_load_2d(sa + 2 * kATileBytes, maps + L.w_map, full_bar(st), koff, n0);
-            tma_load_2d(sa + 2 * kATileBytes + b_bytes, maps + L.w_map + 1, full_bar(st), koff, n0);
+            tma_load_2d_p(sa + 2 * kATileBytes, maps + L.w_map, full_bar(st), koff, n0, el);
+            tma_load_2d_p(sa + 2 * kATileBytes + b_bytes, maps + L.w_map + 1, full_bar(st), koff, n0, el);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one lane) =====
-    if (lane == 0) {
+    // ===== MMA issuer (warp-uniform loops, one elected lane issues) =====
+    const uint32_t el = elect_one();
+    {
       // kind::f16, A/B = bf16 K-major, D = fp32, M = 128, N = ntile
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ntile >> 3) << 17) | ((128u >> 4) << 24);
+      // two MMAs per K atom (see conv_halo.cu): A_hi x [W_hi;W_lo] (N = 2n) and A_lo x W_hi (N = n)
+      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+      const uint32_t idesc1 = idesc_base | ((uint32_t)(ntile >> 3) << 17);
+      const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * ntile) >> 3) << 17);
       int it = 0;
       for (int s = 0; s < L.nseg; ++s) {
         const int cpad = L.seg_cpad[s];
@@ -177,20 +106,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcLayer L, c
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_base + st * stage_bytes;
             const int nk = min(kBlockK, cpad - c0) >> 4;
+            const uint64_t a_hi0 = umma_desc(sa), a_lo0 = umma_desc(sa + kATileBytes);
+            const uint64_t b_hi0 = umma_desc(sa + 2 * kATileBytes);   // lo rows follow the hi rows
+#pragma unroll 4
             for (int ka = 0; ka < nk; ++ka) {
-              const uint64_t a_hi = umma_desc(sa + ka * 32);
-              const uint64_t a_lo = umma_desc(sa + kATileBytes + ka * 32);
-              const uint64_t b_hi = umma_desc(sa + 2 * kATileBytes + ka * 32);
-              const uint64_t b_lo = umma_desc(sa + 2 * kATileBytes + b_bytes + ka * 32);
-              umma_bf16(tmem_d, a_hi, b_hi, idesc, (it > 0 || ka > 0) ? 1u : 0u);
-              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
-              umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+              const uint64_t ko = (uint64_t)(ka * 2);            // 32 bytes per k-atom, in 16-byte units
+              umma_bf16_p(tmem_d, a_hi0 + ko, b_hi0 + ko, idesc2, (it > 0 || ka > 0) ? 1u : 0u, el);
+              umma_bf16_p(tmem_d, a_lo0 + ko, b_hi0 + ko, idesc1, 1u, el);
             }
-            umma_commit(empty_bar(st));   // frees the stage once these MMAs have read it
+            umma_commit_p(empty_bar(st), el);   // frees the stage once these MMAs have read it
           }
         }
       }
-      umma_commit(accum_bar);             // accumulator complete
+      umma_commit_p(accum_bar, el);             // accumulator complete
     }
     __syncwarp();
   } else {
@@ -205,11 +133,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcLayer L, c
     for (int c = 0; c < ntile; c += 16) {
       const int n = n0 + c;
       if (n >= L.cout_store) break;        // warp-uniform
-      float v[16];
+      float v[16], v2[16];
       tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ntile + c), v2);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        v[i] += __ldg(L.bias + n + i);
+        v[i] = (v[i] + v2[i]) + __ldg(L.bias + n + i);
         if (L.relu) v[i] = fmaxf(v[i], 0.f);
       }
       if (!inside) continue;
@@ -240,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcLayer L, c
   }
 }
 
+
 // ------------------------------------------------------------------------------------------
 // host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -259,12 +189,12 @@ static EncodeTiledFn get_encode() {
 }
 
 int tc_encode_act_map(CUtensorMap* out, const void* base, int c, int cstride, int W, int H, int N,
-                      size_t img_stride_elems) {
+                      size_t img_stride_elems, int box_w, int box_h) {
   EncodeTiledFn enc = get_encode();
   PF_REQUIRE(enc, PF_ESTATE, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)cstride * 2, (cuuint64_t)W * cstride * 2, (cuuint64_t)img_stride_elems * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -288,8 +218,14 @@ int tc_encode_weight_map(CUtensorMap* out, const void* base, int ktot, int npad,
   return 0;
 }
 
-void tc_pick_tiling(int coutpad, int* ntile, int* nblocks, int* stages, int* tmem_cols, size_t* smem_bytes) {
-  const int nb = (coutpad + 127) / 128;
+void tc_pick_tiling(int coutpad, int total_tiles, int* ntile, int* nblocks, int* stages, int* tmem_cols,
+                    size_t* smem_bytes) {
+  // N <= 128 per CTA.  Layers with few pixel tiles (low resolution) are split along N as well so
+  // that about one CTA per SM exists: their cost is per-CTA operand streaming, not L2 traffic.
+  int nb = (coutpad + 127) / 128;
+  const int want = kNumSMs / total_tiles;      // never more CTAs than SMs
+  if (want > nb) nb = want;
+  if (nb > coutpad / 16) nb = coutpad / 16;
   int nt = ((coutpad + nb - 1) / nb + 15) / 16 * 16;
   *ntile = nt;
   *nblocks = (coutpad + nt - 1) / nt;
@@ -299,7 +235,7 @@ void tc_pick_tiling(int coutpad, int* ntile, int* nblocks, int* stages, int* tme
   if (s < 2) s = 2;
   *stages = s;
   int cols = 32;
-  while (cols < nt) cols <<= 1;
+  while (cols < 2 * nt) cols <<= 1;
   *tmem_cols = cols;
   *smem_bytes = stage * s + 1024;
 }

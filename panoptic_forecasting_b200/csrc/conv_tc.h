@@ -28,10 +28,40 @@ struct TcLayer {
   const float* bias;
 };
 
+// 3x3 / stride-1 layers on the persistent halo kernel (conv_halo.cu)
+struct HaloLayer {
+  int nseg;
+  int seg_cpad[kMaxSegs];   // channels of each input slice, padded to 16
+  int seg_w[kMaxSegs];      // chunk width of the slice: 16 / 32 / 64 channels (32 / 64 / 128-byte swizzle)
+  int seg_map[kMaxSegs];    // hi-plane halo-box tensor map of the slice (lo = +1)
+  int seg_koff[kMaxSegs];   // first K column of the slice in the packed weight matrix
+  int w_map[3];             // weight tensor maps (hi; lo = +1) for chunk widths 16 / 32 / 64
+  int Hout, Wout, tiles_x, tiles_y, batch;
+  int ntile, tmem_cols, stages_a, stages_b;
+  uint32_t a_tile_bytes, b_tile_bytes;
+  int resident;             // weights stay in shared memory for the whole kernel
+  uint32_t w_bytes_total, w_tx_total;
+  int cout_store, relu;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int out_cs;
+  size_t out_img_stride;
+  const float* bias;
+  long long* dbg_ts;        // optional: CTA 0 writes phase timestamps (clock64) here
+};
+
+int halo_chunk_width(int cpad);
+int halo_encode_act_map(CUtensorMap* out, const void* base, int c, int cstride, int W, int H, int N,
+                        size_t img_stride_elems, int w);
+int halo_encode_weight_map(CUtensorMap* out, const void* base, int ktot, int nrows, int ntile, int w);
+bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes);
+int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblocks, size_t smem_bytes, cudaStream_t st);
+
 int tc_encode_act_map(CUtensorMap* out, const void* base, int c, int cstride, int W, int H, int N,
-                      size_t img_stride_elems);
+                      size_t img_stride_elems, int box_w = 16, int box_h = 8);
 int tc_encode_weight_map(CUtensorMap* out, const void* base, int ktot, int npad, int ntile);
-void tc_pick_tiling(int coutpad, int* ntile, int* nblocks, int* stages, int* tmem_cols, size_t* smem_bytes);
+void tc_pick_tiling(int coutpad, int total_tiles, int* ntile, int* nblocks, int* stages, int* tmem_cols,
+                    size_t* smem_bytes);
 int launch_conv_tc(const TcLayer& L, const CUtensorMap* maps_dev, int nblocks, int batch, size_t smem_bytes,
                    cudaStream_t st);
 

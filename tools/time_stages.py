@@ -44,6 +44,17 @@ def main():
             d, m = timed("decode_depth", lambda: pipe.decode_depth(depth))
             timed("bg.predict", lambda: bg.predict({"seg": seg, "depth": d, "depth_mask": m}, {}))
             timed("forecast", lambda: pipe.forecast(inp))
+            # warp timed inside the full pipeline (L2 holds the previous step's activations)
+            evs = []
+            for _ in range(5):
+                a, b_, c_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a.record(); s2, d2 = pipe.warp(inp); b_.record()
+                dd, mm = pipe.decode_depth(d2); c_.record()
+                bg.predict({"seg": s2, "depth": dd, "depth_mask": mm}, {})
+                evs.append((a, b_, c_))
+            torch.cuda.synchronize()
+            print("  interleaved: warp %.3f ms, disk hop %.3f ms" % (
+                sum(a.elapsed_time(b_) for a, b_, _ in evs) / 5, sum(b_.elapsed_time(c_) for _, b_, c_ in evs) / 5))
 
 
 if __name__ == "__main__":
