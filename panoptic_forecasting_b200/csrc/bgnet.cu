@@ -435,20 +435,40 @@ __global__ void upsample_argmax_kernel(const float* __restrict__ q, int b, int n
     const float hy = 1.f - ly, hx = 1.f - lx;
     float best = -INFINITY;
     int arg = 0;
-    for (int c = 0; c < ncls; ++c) {
-      float v00, v01, v10, v11;
-      if (NHWC16) {
-        const float* base = q + (size_t)img * h * w * 16 + c;
-        v00 = base[((size_t)y0 * w + x0) * 16]; v01 = base[((size_t)y0 * w + x1) * 16];
-        v10 = base[((size_t)y1 * w + x0) * 16]; v11 = base[((size_t)y1 * w + x1) * 16];
-      } else {
-        const float* base = q + ((size_t)img * ncls + c) * h * w;
-        v00 = base[(size_t)y0 * w + x0]; v01 = base[(size_t)y0 * w + x1];
-        v10 = base[(size_t)y1 * w + x0]; v11 = base[(size_t)y1 * w + x1];
+    if (NHWC16) {
+      // 16 fp32 logits per quarter-res pixel: four 128-bit loads per corner, classes in registers
+      const float4* p00 = reinterpret_cast<const float4*>(q + ((size_t)img * h * w + (size_t)y0 * w + x0) * 16);
+      const float4* p01 = reinterpret_cast<const float4*>(q + ((size_t)img * h * w + (size_t)y0 * w + x1) * 16);
+      const float4* p10 = reinterpret_cast<const float4*>(q + ((size_t)img * h * w + (size_t)y1 * w + x0) * 16);
+      const float4* p11 = reinterpret_cast<const float4*>(q + ((size_t)img * h * w + (size_t)y1 * w + x1) * 16);
+      const int nq = (ncls + 3) >> 2;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k >= nq) break;
+        const float4 a = __ldg(p00 + k), b_ = __ldg(p01 + k), c_ = __ldg(p10 + k), d = __ldg(p11 + k);
+        float v[4];
+        v[0] = hy * (hx * a.x + lx * b_.x) + ly * (hx * c_.x + lx * d.x);
+        v[1] = hy * (hx * a.y + lx * b_.y) + ly * (hx * c_.y + lx * d.y);
+        v[2] = hy * (hx * a.z + lx * b_.z) + ly * (hx * c_.z + lx * d.z);
+        v[3] = hy * (hx * a.w + lx * b_.w) + ly * (hx * c_.w + lx * d.w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = k * 4 + j;
+          if (c < ncls) {
+            if (full) full[(((size_t)img * ncls + c) * fh + y) * fw + x] = v[j];
+            if (v[j] > best) { best = v[j]; arg = c; }
+          }
+        }
       }
-      const float v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
-      if (full) full[(((size_t)img * ncls + c) * fh + y) * fw + x] = v;
-      if (v > best) { best = v; arg = c; }
+    } else {
+      for (int c = 0; c < ncls; ++c) {
+        const float* base = q + ((size_t)img * ncls + c) * h * w;
+        const float v00 = base[(size_t)y0 * w + x0], v01 = base[(size_t)y0 * w + x1];
+        const float v10 = base[(size_t)y1 * w + x0], v11 = base[(size_t)y1 * w + x1];
+        const float v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+        if (full) full[(((size_t)img * ncls + c) * fh + y) * fw + x] = v;
+        if (v > best) { best = v; arg = c; }
+      }
     }
     if (seg8) seg8[i] = (uint8_t)arg;
     if (seg64) seg64[i] = arg;
@@ -698,8 +718,10 @@ static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUte
 static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUtensorMap>* maps, HaloLayer* L,
                             int* nblocks, size_t* smem) {
   const ConvDesc& c = net->convs[i];
-  if (c.ksize != 3 || c.stride != 1 || io.out_f32) return 1;
+  if (c.stride != 1) return 1;
   memset(L, 0, sizeof(*L));
+  const int taps = c.ksize * c.ksize;
+  L->taps = taps; L->hx = c.ksize == 3 ? 10 : 8; L->hy = c.ksize == 3 ? 18 : 16;
   int ntile, nb, stages, cols;
   size_t dummy;
   tc_pick_tiling(c.coutpad, cdiv(io.Wout, 8) * cdiv(io.Hout, 16) * io.b, &ntile, &nb, &stages, &cols, &dummy);
@@ -713,20 +735,20 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     L->seg_w[s] = halo_chunk_width(cp);
     used[L->seg_w[s] >> 5] = true;
     L->seg_koff[s] = kb;
-    kb += 9 * cp;
+    kb += taps * cp;
   }
   if (!halo_plan_smem(L, smem)) return 1;
   for (int s = 0; s < L->nseg; ++s) {
     L->seg_map[s] = (int)maps->size();
     CUtensorMap m;
-    int rc = halo_encode_act_map(&m, io.in_hi[s], L->seg_cpad[s], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[s]);
+    int rc = halo_encode_act_map(&m, io.in_hi[s], L->seg_cpad[s], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[s], L->hx, L->hy);
     if (rc) return rc;
     maps->push_back(m);
-    rc = halo_encode_act_map(&m, io.in_lo[s], L->seg_cpad[s], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[s]);
+    rc = halo_encode_act_map(&m, io.in_lo[s], L->seg_cpad[s], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[s], L->hx, L->hy);
     if (rc) return rc;
     maps->push_back(m);
   }
-  const int ktot = 9 * c.kpad;
+  const int ktot = taps * c.kpad;
   const int nrows = net->wtc_rows[i];
   for (int k = 0; k < 3; ++k) {
     L->w_map[k] = -1;
@@ -747,10 +769,11 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   int tcols = 32;
   while (tcols < 4 * ntile) tcols <<= 1;
   L->tmem_cols = tcols;
-  L->cout_store = padc(c.cout);
+  L->cout_store = io.out_f32 ? 16 : padc(c.cout);
   L->relu = c.relu ? 1 : 0;
   L->out_hi = reinterpret_cast<__nv_bfloat16*>(io.out_hi);
   L->out_lo = reinterpret_cast<__nv_bfloat16*>(io.out_lo);
+  L->out_f32 = io.out_f32;
   L->out_cs = io.out_cs; L->out_img_stride = io.out_img;
   L->bias = c.bias_dev;
   return 0;

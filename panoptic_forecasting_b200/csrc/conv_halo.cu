@@ -28,7 +28,6 @@ namespace pf {
 using namespace tc;
 
 namespace {
-constexpr int kHX = 10, kHY = 18;               // halo box: 18 rows x 10 columns of input pixels
 constexpr int kMaxA = 4, kMaxB = 8;
 
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
@@ -70,6 +69,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
   const int n0 = blockIdx.y * ntile;
   const int tiles_per_img = L.tiles_x * L.tiles_y;
   const int total_tiles = tiles_per_img * L.batch;
+  const int HX = L.hx, HY = L.hy, NT = L.taps;     // 3x3: 10 x 18 box, 9 taps; 1x1: 8 x 16 box, 1 tap
+  const int org = NT == 9 ? 1 : 0;                  // box origin = tile origin - pad
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
           const CUtensorMap* wm = maps + L.w_map[w >> 5];          // 16 -> 0, 32 -> 1, 64 -> 2
           const uint32_t bt = (uint32_t)ntile * 2u * w;            // hi rows, lo rows directly behind them
           for (int c0 = 0; c0 < cpad; c0 += w)
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < NT; ++tap) {
               const int koff = L.seg_koff[s] + tap * cpad + c0;
               tma_load_2d_p(smem_base + off, wm, wbar, koff, n0, el);
               tma_load_2d_p(smem_base + off + bt, wm + 1, wbar, koff, n0, el);
@@ -119,17 +120,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
           const int cpad = L.seg_cpad[s], w = L.seg_w[s];
           const CUtensorMap* am = maps + L.seg_map[s];
           const CUtensorMap* wm = maps + L.w_map[w >> 5];
-          const uint32_t a_tx = (uint32_t)kHX * kHY * 2u * w;
+          const uint32_t a_tx = (uint32_t)(HX * HY) * 2u * w;
           const uint32_t b_tx = (uint32_t)ntile * 2u * w;
           for (int c0 = 0; c0 < cpad; c0 += w, ++ia) {
             const int st = ia % SA;
             mbar_wait(empty_a(st), ((ia / SA) & 1) ^ 1);
             const uint32_t sa = a_base + st * 2 * a_tile;
             mbar_expect_tx_p(full_a(st), 2 * a_tx, el);
-            tma_load_4d_p(sa, am, full_a(st), c0, x0 - 1, y0 - 1, img, el);
-            tma_load_4d_p(sa + a_tile, am + 1, full_a(st), c0, x0 - 1, y0 - 1, img, el);
+            tma_load_4d_p(sa, am, full_a(st), c0, x0 - org, y0 - org, img, el);
+            tma_load_4d_p(sa + a_tile, am + 1, full_a(st), c0, x0 - org, y0 - org, img, el);
             if (!L.resident) {
-              for (int tap = 0; tap < 9; ++tap, ++ib) {
+              for (int tap = 0; tap < NT; ++tap, ++ib) {
                 const int sb = ib % SB;
                 mbar_wait(empty_b(sb), ((ib / SB) & 1) ^ 1);
                 const uint32_t sbp = b_base + sb * b_tile;
@@ -178,12 +179,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
             const int nk = min(w, cpad - c0) >> 4;
             // descriptors are linear in the start address: build the chunk's base descriptors once,
             // then every (tap, k-atom) is one 64-bit add (the MMA issuer is a single thread).
-            const uint64_t a_hi0 = desc_kmajor(sa, kHX * rp, lay);
-            const uint64_t a_lo0 = desc_kmajor(sa + a_tile, kHX * rp, lay);
+            const uint64_t a_hi0 = desc_kmajor(sa, HX * rp, lay);
+            const uint64_t a_lo0 = desc_kmajor(sa + a_tile, HX * rp, lay);
             const uint32_t tap_step = rp >> 4;                   // one pixel row, in 16-byte units
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < NT; ++tap) {
               const int dy = tap / 3, dx = tap - dy * 3;
-              const uint64_t shift = (uint64_t)((dy * kHX + dx) * tap_step);
+              const uint64_t shift = (uint64_t)((dy * HX + dx) * tap_step);
               uint32_t sb_hi;
               int sbi = 0;
               if (L.resident) {
@@ -243,6 +244,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
           if (L.relu) v[i] = fmaxf(v[i], 0.f);
         }
         if (!inside) continue;
+        if (L.out_f32) {
+          float4* o = reinterpret_cast<float4*>(L.out_f32 + pix + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          continue;
+        }
         uint4 h[2], l[2];
         uint2 th, tl;
 #pragma unroll
@@ -293,12 +300,12 @@ static EncodeTiledFn get_encode2() {
 }
 
 int halo_encode_act_map(CUtensorMap* out, const void* base, int c, int cstride, int W, int H, int N,
-                        size_t img_stride_elems, int w) {
+                        size_t img_stride_elems, int w, int hx, int hy) {
   EncodeTiledFn enc = get_encode2();
   PF_REQUIRE(enc, PF_ESTATE, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)cstride * 2, (cuuint64_t)W * cstride * 2, (cuuint64_t)img_stride_elems * 2};
-  cuuint32_t box[4] = {(cuuint32_t)w, (cuuint32_t)kHX, (cuuint32_t)kHY, 1};
+  cuuint32_t box[4] = {(cuuint32_t)w, (cuuint32_t)hx, (cuuint32_t)hy, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(w), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -333,10 +340,10 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
     if (w > wmax) wmax = w;
     const int nchunks = (L->seg_cpad[s] + w - 1) / w;
     const size_t bt = align_up((size_t)2 * L->ntile * 2 * w, 1024);   // [hi rows ; lo rows] of one tap
-    w_total += (size_t)nchunks * 9 * bt;
-    w_tx += (size_t)nchunks * 9 * 2 * (size_t)L->ntile * 2 * w;
+    w_total += (size_t)nchunks * L->taps * bt;
+    w_tx += (size_t)nchunks * L->taps * 2 * (size_t)L->ntile * 2 * w;
   }
-  const size_t a_tile = align_up((size_t)kHX * kHY * 2 * wmax, 1024);
+  const size_t a_tile = align_up((size_t)L->hx * L->hy * 2 * wmax, 1024);
   const size_t b_tile = align_up((size_t)2 * L->ntile * 2 * wmax, 1024);
   L->a_tile_bytes = (uint32_t)a_tile;
   L->b_tile_bytes = (uint32_t)b_tile;

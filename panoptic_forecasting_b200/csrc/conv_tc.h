@@ -37,6 +37,7 @@ struct HaloLayer {
   int seg_koff[kMaxSegs];   // first K column of the slice in the packed weight matrix
   int w_map[3];             // weight tensor maps (hi; lo = +1) for chunk widths 16 / 32 / 64
   int Hout, Wout, tiles_x, tiles_y, batch;
+  int taps, hx, hy;         // 9 taps / 10 x 18 box (3x3) or 1 tap / 8 x 16 box (1x1)
   int ntile, tmem_cols, stages_a, stages_b;
   uint32_t a_tile_bytes, b_tile_bytes;
   int resident;             // weights stay in shared memory for the whole kernel
@@ -44,6 +45,7 @@ struct HaloLayer {
   int cout_store, relu;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
+  float* out_f32;           // if set: fp32 output (head), no split
   int out_cs;
   size_t out_img_stride;
   const float* bias;
@@ -52,7 +54,7 @@ struct HaloLayer {
 
 int halo_chunk_width(int cpad);
 int halo_encode_act_map(CUtensorMap* out, const void* base, int c, int cstride, int W, int H, int N,
-                        size_t img_stride_elems, int w);
+                        size_t img_stride_elems, int w, int hx, int hy);
 int halo_encode_weight_map(CUtensorMap* out, const void* base, int ktot, int nrows, int ntile, int w);
 bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes);
 int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblocks, size_t smem_bytes, cudaStream_t st);
