@@ -279,25 +279,48 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(FirstParams p) {
   const int oy0 = ty * F_TH, ox0 = tx * F_TW;
   const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
   const size_t N = (size_t)p.H * p.W;
-  for (int i = tid; i < p.t * F_IH * F_IW; i += blockDim.x) {
-    const int f = i / (F_IH * F_IW);
-    const int r = i % (F_IH * F_IW);
-    const int hy = r / F_IW, hx = r % F_IW;
-    const int iy = iy0 + hy, ix = ix0 + hx;
-    uint8_t l = (uint8_t)p.ncls;   // zero row: padding or class id >= num_classes
-    float d = 0.f;
-    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-      const size_t o = ((size_t)img * p.t + f) * N + (size_t)iy * p.W + ix;
-      uint8_t lv = p.labels[o];
-      if (lv < p.ncls) l = lv;
-      if (p.use_depth) {
-        // bg_model.py:50-51,67-68: (d - mean) / std, then * mask
-        float v = __fdiv_rn(__fadd_rn(p.depth[o], -p.mean), p.std);
-        d = p.mask[o] ? v : __fmul_rn(v, 0.0f);
+  // stage the (2*8+1) x (2*32+1) x t input window; loads are issued four at a time per thread before
+  // any of them is consumed (the kernel is otherwise bound by global-load latency here)
+  const int n_in = p.t * F_IH * F_IW;
+  for (int i0 = tid; i0 < n_in; i0 += 4 * (int)blockDim.x) {
+    uint8_t lv[4], mv[4];
+    float dv[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * (int)blockDim.x;
+      ok[j] = false;
+      lv[j] = 0; mv[j] = 0; dv[j] = 0.f;
+      if (i < n_in) {
+        const int f = i / (F_IH * F_IW);
+        const int r = i - f * (F_IH * F_IW);
+        const int hy = r / F_IW, hx = r - hy * F_IW;
+        const int iy = iy0 + hy, ix = ix0 + hx;
+        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          const size_t o = ((size_t)img * p.t + f) * N + (size_t)iy * p.W + ix;
+          ok[j] = true;
+          lv[j] = __ldg(p.labels + o);
+          if (p.use_depth) { dv[j] = __ldg(p.depth + o); mv[j] = __ldg(p.mask + o); }
+        }
       }
     }
-    lab[i] = l;
-    dn[i] = d;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * (int)blockDim.x;
+      if (i >= n_in) break;
+      uint8_t l = (uint8_t)p.ncls;   // zero row: padding or class id >= num_classes
+      float d = 0.f;
+      if (ok[j]) {
+        if (lv[j] < p.ncls) l = lv[j];
+        if (p.use_depth) {
+          // bg_model.py:50-51,67-68: (d - mean) / std, then * mask
+          const float v = __fdiv_rn(__fadd_rn(dv[j], -p.mean), p.std);
+          d = mv[j] ? v : __fmul_rn(v, 0.0f);
+        }
+      }
+      lab[i] = l;
+      dn[i] = d;
+    }
   }
   __syncthreads();
   const int py = tid / F_TW, px = tid % F_TW;
@@ -356,17 +379,15 @@ __global__ void avgpool2_kernel(PoolParams p) {
     const int y = (int)(r % p.Ho);
     const int img = (int)(r / p.Ho);
     const int Wi = p.Wo * 2;
-    const size_t p0 = img * p.in_img + ((size_t)(2 * y) * Wi + 2 * x) * p.in_cs + c * 4;
-    const float4 a = load4_any(p.in, p.in_lo, p0, sp);
-    const float4 bq = load4_any(p.in, p.in_lo, p0 + p.in_cs, sp);
-    const float4 cq = load4_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs, sp);
-    const float4 d = load4_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs + p.in_cs, sp);
-    float4 o;
-    o.x = (a.x + bq.x + cq.x + d.x) * 0.25f;
-    o.y = (a.y + bq.y + cq.y + d.y) * 0.25f;
-    o.z = (a.z + bq.z + cq.z + d.z) * 0.25f;
-    o.w = (a.w + bq.w + cq.w + d.w) * 0.25f;
-    store4_any(p.out, p.out_lo, img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + c * 4, o, sp);
+    const size_t p0 = img * p.in_img + ((size_t)(2 * y) * Wi + 2 * x) * p.in_cs + c * 8;
+    float a[8], bq[8], cq[8], d[8], o[8];
+    load8_any(p.in, p.in_lo, p0, sp, a);
+    load8_any(p.in, p.in_lo, p0 + p.in_cs, sp, bq);
+    load8_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs, sp, cq);
+    load8_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs + p.in_cs, sp, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (a[k] + bq[k] + cq[k] + d[k]) * 0.25f;
+    store8_any(p.out, p.out_lo, img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + c * 8, o, sp);
   }
 }
 
@@ -385,7 +406,7 @@ __global__ void upsample_bilinear_kernel(UpParams p) {
   const size_t total = (size_t)p.b * p.Ho * p.Wo * p.c4_total;
   const bool sp = p.split != 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % p.c4_total) * 4;
+    int c = (int)(i % p.c4_total) * 8;
     size_t r = i / p.c4_total;
     const int x = (int)(r % p.Wo); r /= p.Wo;
     const int y = (int)(r % p.Ho);
@@ -402,16 +423,14 @@ __global__ void upsample_bilinear_kernel(UpParams p) {
     const int cs = p.segs[s].cstride;
     const void* bh = p.segs[s].base;
     const void* bl = p.segs[s].base_lo;
-    const float4 v00 = load4_any(bh, bl, base + ((size_t)y0 * p.Wi + x0) * cs, sp);
-    const float4 v01 = load4_any(bh, bl, base + ((size_t)y0 * p.Wi + x1) * cs, sp);
-    const float4 v10 = load4_any(bh, bl, base + ((size_t)y1 * p.Wi + x0) * cs, sp);
-    const float4 v11 = load4_any(bh, bl, base + ((size_t)y1 * p.Wi + x1) * cs, sp);
-    float4 o;
-    o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-    o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
-    o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
-    o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    store4_any(p.out, p.out_lo, img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + cout, o, sp);
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    load8_any(bh, bl, base + ((size_t)y0 * p.Wi + x0) * cs, sp, v00);
+    load8_any(bh, bl, base + ((size_t)y0 * p.Wi + x1) * cs, sp, v01);
+    load8_any(bh, bl, base + ((size_t)y1 * p.Wi + x0) * cs, sp, v10);
+    load8_any(bh, bl, base + ((size_t)y1 * p.Wi + x1) * cs, sp, v11);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]);
+    store8_any(p.out, p.out_lo, img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + cout, o, sp);
   }
 }
 
@@ -1039,7 +1058,7 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         p.in = a.ptr(in.buf, in.coff); p.in_lo = a.ptr_lo(in.buf, in.coff); p.in_cs = ib.cstride; p.in_img = a.img_elems[in.buf];
         p.out = a.ptr(s.out.buf, s.out.coff); p.out_lo = a.ptr_lo(s.out.buf, s.out.coff); p.out_cs = ob.cstride;
         p.out_img = a.img_elems[s.out.buf];
-        p.b = b; p.Ho = H >> ob.shift; p.Wo = W >> ob.shift; p.c4 = in.cpad() / 4; p.split = split;
+        p.b = b; p.Ho = H >> ob.shift; p.Wo = W >> ob.shift; p.c4 = in.cpad() / 8; p.split = split;
         const size_t total = (size_t)b * p.Ho * p.Wo * p.c4;
         avgpool2_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
         PF_CHECK_CUDA(cudaGetLastError());
@@ -1063,7 +1082,7 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         p.out = a.ptr(s.out.buf, 0); p.out_lo = a.ptr_lo(s.out.buf, 0); p.out_cs = ob.cstride;
         p.out_img = a.img_elems[s.out.buf];
         p.b = b; p.Hi = H >> ib.shift; p.Wi = W >> ib.shift; p.Ho = H >> ob.shift; p.Wo = W >> ob.shift;
-        p.c4_total = ctot / 4; p.split = split;
+        p.c4_total = ctot / 8; p.split = split;
         p.sh = p.Ho > 1 ? (float)(p.Hi - 1) / (float)(p.Ho - 1) : 0.f;
         p.sw = p.Wo > 1 ? (float)(p.Wi - 1) / (float)(p.Wo - 1) : 0.f;
         const size_t total = (size_t)b * p.Ho * p.Wo * p.c4_total;

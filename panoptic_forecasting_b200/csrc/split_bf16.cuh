@@ -47,4 +47,32 @@ __device__ __forceinline__ void store4_any(void* base, void* base_lo, size_t off
   }
 }
 
+// 8 consecutive channels (128-bit loads/stores on the bf16 planes)
+__device__ __forceinline__ void load8_any(const void* base, const void* base_lo, size_t off, bool split, float* v) {
+  if (!split) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    return;
+  }
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+  const uint4 l = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base_lo) + off));
+  v[0] = bf16lo(h.x) + bf16lo(l.x); v[1] = bf16hi(h.x) + bf16hi(l.x);
+  v[2] = bf16lo(h.y) + bf16lo(l.y); v[3] = bf16hi(h.y) + bf16hi(l.y);
+  v[4] = bf16lo(h.z) + bf16lo(l.z); v[5] = bf16hi(h.z) + bf16hi(l.z);
+  v[6] = bf16lo(h.w) + bf16lo(l.w); v[7] = bf16hi(h.w) + bf16hi(l.w);
+}
+__device__ __forceinline__ void store8_any(void* base, void* base_lo, size_t off, const float* v, bool split) {
+  if (!split) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    return;
+  }
+  uint2 h0, l0, h1, l1;
+  split_store4(make_float4(v[0], v[1], v[2], v[3]), &h0, &l0);
+  split_store4(make_float4(v[4], v[5], v[6], v[7]), &h1, &l1);
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base_lo) + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+
 }  // namespace pf

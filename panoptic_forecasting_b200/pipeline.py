@@ -84,3 +84,60 @@ class BGForecastPipeline:
         out = self.bg.predict({'seg': seg, 'depth': d, 'depth_mask': m}, {})
         out['warped_seg'], out['warped_depth'], out['warped_mask'] = seg, d, m
         return out
+
+
+class PipelinedForecaster:
+    """Host-buffer front end for throughput runs: uploads of batch i+1 (copy stream) overlap the
+    forecast of batch i (compute stream) and the download of batch i-1's label map.
+
+    Every submitted batch still pays its own host->device copy (from pinned memory) and its own
+    device->host read of the uint8 label map; they are simply overlapped across batches, which is
+    how an export loop over a dataset runs (reference loop: export_cityscapes_segmentation_results.py:75-110).
+    """
+
+    def __init__(self, pipe, depth=2):
+        self.pipe = pipe
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream()
+        self.compute_stream = torch.cuda.Stream()
+        self.slots = [None] * depth          # device input dicts
+        self.out_host = [None] * depth       # pinned uint8 label maps
+        self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.n_submitted = 0
+        self.n_collected = 0
+
+    def submit(self, host_inputs):
+        """host_inputs: dict of pinned CPU tensors (PCTransformModel input dict)."""
+        s = self.n_submitted % self.depth
+        if self.n_submitted - self.n_collected >= self.depth:
+            raise RuntimeError("pipeline full: collect() before submitting more")
+        dev = self.pipe.bg.depth_mean.device if self.pipe.bg.use_depth_inps else torch.device("cuda")
+        if self.slots[s] is None:
+            self.slots[s] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_inputs.items()}
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[s])          # slot's previous consumer finished
+            for k, v in host_inputs.items():
+                self.slots[s][k].copy_(v, non_blocking=True)
+            self.h2d_done[s].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(self.h2d_done[s])
+            out = self.pipe.forecast(self.slots[s])
+            self.free[s].record(self.compute_stream)
+            seg = out['seg']
+            if self.out_host[s] is None or self.out_host[s].shape != seg.shape:
+                self.out_host[s] = torch.empty(seg.shape, dtype=seg.dtype).pin_memory()
+            self.out_host[s].copy_(seg, non_blocking=True)
+            self.done[s].record(self.compute_stream)
+        self.n_submitted += 1
+
+    def collect(self):
+        """Blocks until the oldest in-flight batch is on the host; returns its pinned label map
+        (valid until the slot is reused `depth` submits later)."""
+        if self.n_collected >= self.n_submitted:
+            raise RuntimeError("nothing in flight")
+        s = self.n_collected % self.depth
+        self.done[s].synchronize()
+        self.n_collected += 1
+        return self.out_host[s]

@@ -51,3 +51,28 @@ def test_composite_matches_composite_oracle(pf_lib, bg_shapes, b, h, w):
     assert torch.equal(out["warped_depth"].cpu(), bg_in["depth"])
     assert torch.equal(out["warped_mask"].cpu().bool(), bg_in["depth_mask"])
     check_against(out, ref, rel_tol=1e-4)
+
+
+def test_pipelined_forecaster_equals_direct(pf_lib, bg_shapes):
+    """Host-buffer pipelined front end (bench.py's e2e path) returns the same label maps as forecast()."""
+    from panoptic_forecasting_b200.pipeline import PipelinedForecaster
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=3)
+    bg = build_model(dict(bg_params(return_logits=False, seg_dtype="uint8"), no_gpu=False)).eval()
+    bg.load_state_dict(sd)
+    pipe = BGForecastPipeline(bg)
+    sets = []
+    for seed in range(3):
+        d = synthetic.make_pc_inputs(b=2, t=3, h=64, w=128, dist="R", seed=seed)
+        d["intrinsics_inv"] = torch.inverse(d["intrinsics"]).contiguous()
+        d["extrinsics_inv"] = torch.inverse(d["extrinsics"]).contiguous()
+        sets.append({k: v.pin_memory() for k, v in d.items()})
+    direct = [pipe.forecast({k: v.cuda() for k, v in s.items()})["seg"].cpu() for s in sets]
+    pf = PipelinedForecaster(pipe, depth=2)
+    got = []
+    for i in range(5):
+        pf.submit(sets[i % 3])
+        if i >= 1:
+            got.append(pf.collect().clone())
+    got.append(pf.collect().clone())
+    for i in range(5):
+        assert torch.equal(got[i], direct[i % 3])
