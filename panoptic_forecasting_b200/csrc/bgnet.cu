@@ -153,17 +153,23 @@ static void build_topology(pf_bgnet* net) {
   const int t = net->num_inputs;
   const int cin0 = (net->num_classes + (net->use_depth ? 1 : 0)) * t;
   // stem (hardnet.py:275-280)
+  // tensor-core storage: base.1 writes space-to-depth (quarter resolution, 4 x 32 channels), see ConvDesc::s2d_out
+  const bool s2d = net->precision == 1;
   int s0 = net->new_buf(1, padc(kFirstCh[0]));
-  int s1 = net->new_buf(1, padc(kFirstCh[1]));
+  int s1 = s2d ? net->new_buf(2, 128) : net->new_buf(1, padc(kFirstCh[1]));
   int s2 = net->new_buf(2, padc(kFirstCh[2]));
   SegRef r0{s0, 0, kFirstCh[0]}, r1{s1, 0, kFirstCh[1]}, r2{s2, 0, kFirstCh[2]};
+  SegRef r1_in = r1;
+  if (s2d) r1_in.c = 128;
   {
     int ci = net->add_conv("model.base.0", cin0, kFirstCh[0], 3, 2, {}, r0);
     net->first_conv = ci;
     Step st; st.type = STEP_FIRST; st.conv = ci; net->steps.push_back(st);
     ci = net->add_conv("model.base.1", kFirstCh[0], kFirstCh[1], 3, 1, {r0}, r1);
+    net->convs[ci].s2d_out = s2d;
     st.type = STEP_CONV; st.conv = ci; net->steps.push_back(st);
-    ci = net->add_conv("model.base.2", kFirstCh[1], kFirstCh[2], 3, 2, {r1}, r2);
+    ci = net->add_conv("model.base.2", kFirstCh[1], kFirstCh[2], 3, 2, {r1_in}, r2);
+    net->convs[ci].s2d_in = s2d;
     st.conv = ci; net->steps.push_back(st);
   }
   // base.3 writes straight into encoder block 0's input slot; patched after the block exists.
@@ -548,6 +554,39 @@ __global__ void nhwc_to_nchw_kernel(const void* in, const void* in_lo, int split
   }
 }
 
+// debug helpers for the space-to-depth layers (split-bf16 storage, 4 phase blocks of 32 channels)
+__global__ void nchw_to_s2d_kernel(const float* __restrict__ in, unsigned short* out, unsigned short* out_lo, int b, int c,
+                                   int h, int w) {
+  const size_t total = (size_t)b * (h / 2) * (w / 2) * 128;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % 128);
+    size_t r = i / 128;
+    const int X = (int)(r % (w / 2)); r /= (w / 2);
+    const int Y = (int)(r % (h / 2));
+    const int img = (int)(r / (h / 2));
+    const int blk = ch / 32, cc = ch % 32;
+    const int y = 2 * Y + (blk >> 1), x = 2 * X + (blk & 1);
+    const float v = cc < c ? in[(((size_t)img * c + cc) * h + y) * w + x] : 0.f;
+    unsigned hi, lo;
+    split1(v, &hi, &lo);
+    out[i] = (unsigned short)hi;
+    out_lo[i] = (unsigned short)lo;
+  }
+}
+__global__ void s2d_to_nchw_kernel(const unsigned short* in, const unsigned short* in_lo, float* __restrict__ out, int b,
+                                   int c, int h, int w) {
+  const size_t total = (size_t)b * c * h * w;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    size_t r = i / w;
+    const int y = (int)(r % h); r /= h;
+    const int ch = (int)(r % c);
+    const int img = (int)(r / c);
+    const size_t o = (((size_t)img * (h / 2) + (y >> 1)) * (w / 2) + (x >> 1)) * 128 + ((y & 1) * 2 + (x & 1)) * 32 + ch;
+    out[i] = __uint_as_float((unsigned)in[o] << 16) + __uint_as_float((unsigned)in_lo[o] << 16);
+  }
+}
+
 static int grid_for(size_t total, int threads) {
   size_t g = (total + threads - 1) / threads;
   const size_t cap = (size_t)kNumSMs * 16;
@@ -621,6 +660,12 @@ static void fill_conv_launch(const pf_bgnet* net, const Arena& a, const ConvDesc
   L->kpad = c.kpad; L->coutpad = c.coutpad;
   L->cout_store = padc(c.cout);
   L->relu = c.relu ? 1 : 0;
+  L->s2d_block = 0;
+  if (c.s2d_out) {                     // output buffer is the quarter-res space-to-depth tensor
+    L->Hout = L->Hin; L->Wout = L->Win;
+    L->s2d_block = 32;
+    L->cout_store = 32;
+  }
 }
 
 // ---- tensor-core path helpers --------------------------------------------------------------
@@ -684,7 +729,7 @@ struct TcIo {                       // where one conv reads and writes (arena or
 static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUtensorMap>* maps, TcLayer* L,
                           int* nblocks, size_t* smem) {
   const ConvDesc& c = net->convs[i];
-  PF_REQUIRE(c.stride == 1, PF_EINVAL, "build_tc_layer: stride-2 convs run on the SIMT kernel");
+  PF_REQUIRE(c.stride == 1 && !c.s2d_out, PF_EINVAL, "build_tc_layer: layer needs the halo or SIMT kernel");
   memset(L, 0, sizeof(*L));
   const int taps = c.ksize * c.ksize;
   L->nseg = (int)c.in.size();
@@ -722,7 +767,7 @@ static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUte
   L->Hout = io.Hout; L->Wout = io.Wout;
   L->tiles_x = cdiv(io.Wout, 16); L->tiles_y = cdiv(io.Hout, 8);
   L->ntile = ntile; L->stages = stages; L->tmem_cols = cols;
-  L->cout_store = io.out_f32 ? 16 : padc(c.cout);
+  L->cout_store = io.out_f32 ? 16 : (c.s2d_out ? 32 : padc(c.cout));
   L->relu = c.relu ? 1 : 0;
   L->out_hi = reinterpret_cast<__nv_bfloat16*>(io.out_hi);
   L->out_lo = reinterpret_cast<__nv_bfloat16*>(io.out_lo);
@@ -737,10 +782,12 @@ static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUte
 static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUtensorMap>* maps, HaloLayer* L,
                             int* nblocks, size_t* smem) {
   const ConvDesc& c = net->convs[i];
-  if (c.stride != 1) return 1;
+  if (c.exec_stride() != 1) return 1;
   memset(L, 0, sizeof(*L));
   const int taps = c.ksize * c.ksize;
   L->taps = taps; L->hx = c.ksize == 3 ? 10 : 8; L->hy = c.ksize == 3 ? 18 : 16;
+  L->tap_mask = c.s2d_in ? 0x1B : (1 << taps) - 1;
+  L->s2d_block = c.s2d_out ? 32 : 0;
   int ntile, nb, stages, cols;
   size_t dummy;
   tc_pick_tiling(c.coutpad, cdiv(io.Wout, 8) * cdiv(io.Hout, 16) * io.b, &ntile, &nb, &stages, &cols, &dummy);
@@ -788,7 +835,7 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   int tcols = 32;
   while (tcols < 4 * ntile) tcols <<= 1;
   L->tmem_cols = tcols;
-  L->cout_store = io.out_f32 ? 16 : padc(c.cout);
+  L->cout_store = io.out_f32 ? 16 : (c.s2d_out ? 32 : padc(c.cout));
   L->relu = c.relu ? 1 : 0;
   L->out_hi = reinterpret_cast<__nv_bfloat16*>(io.out_hi);
   L->out_lo = reinterpret_cast<__nv_bfloat16*>(io.out_lo);
@@ -810,7 +857,7 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
   P.use_tc.assign(nc, 0);
   for (size_t i = 0; i < nc; ++i) {
     const ConvDesc& c = net->convs[i];
-    if ((int)i == net->first_conv || c.stride != 1) continue;
+    if ((int)i == net->first_conv || c.exec_stride() != 1) continue;
     TcIo io;
     for (size_t s = 0; s < c.in.size(); ++s) {
       const SegRef& r = c.in[s];
@@ -820,12 +867,14 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
     const BufDesc& ib = net->bufs[c.in[0].buf];
     const BufDesc& ob = net->bufs[c.out.buf];
     io.Hin = a.H >> ib.shift; io.Win = a.W >> ib.shift; io.Hout = a.H >> ob.shift; io.Wout = a.W >> ob.shift; io.b = a.b;
+    if (c.s2d_out) { io.Hout = io.Hin; io.Wout = io.Win; }
     const bool head = (int)i == net->final_conv;
     io.out_hi = head ? nullptr : a.ptr(c.out.buf, c.out.coff);
     io.out_lo = head ? nullptr : a.ptr_lo(c.out.buf, c.out.coff);
     io.out_f32 = head ? reinterpret_cast<float*>(a.ptr(c.out.buf, c.out.coff)) : nullptr;
     io.out_cs = ob.cstride; io.out_img = a.img_elems[c.out.buf];
-    int rc = net->no_halo ? 1 : build_halo_layer(net, (int)i, io, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i]);
+    const bool need_halo = c.s2d_in || c.s2d_out;
+    int rc = (net->no_halo && !need_halo) ? 1 : build_halo_layer(net, (int)i, io, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i]);
     if (rc == 0) { P.use_tc[i] = 2; continue; }
     if (rc != 1) return rc;
     rc = build_tc_layer(net, (int)i, io, &maps, &P.layers[i], &P.nblocks[i], &P.smem[i]);
@@ -916,6 +965,19 @@ static int upload_conv(pf_bgnet* net, int i, const std::vector<double>& wfold /*
   c.w_host.assign((size_t)taps * c.kpad * c.coutpad, 0.f);
   c.bias_host.assign(c.coutpad, 0.f);
   int kp = 0, ci = 0;
+  if (c.s2d_in) {
+    // original tap d in {0,1,2} reads input row 2Y+d-1 = quarter-res row Y+t, phase p: d=0 -> (t=-1,p=1),
+    // d=1 -> (t=0,p=0), d=2 -> (t=0,p=1).  Virtual 3x3 tap index = (t+1)*3 + ..., channel = phase block * 32 + c.
+    static const int tmap[3] = {0, 1, 1}, pmap[3] = {1, 0, 1};
+    for (int dy = 0; dy < 3; ++dy)
+      for (int dx = 0; dx < 3; ++dx) {
+        const int vt = tmap[dy] * 3 + tmap[dx];
+        const int blk = pmap[dy] * 2 + pmap[dx];
+        for (int ch = 0; ch < c.cin; ++ch)
+          for (int o = 0; o < c.cout; ++o)
+            c.w_host[((size_t)vt * c.kpad + blk * 32 + ch) * c.coutpad + o] = (float)wfold[((size_t)o * c.cin + ch) * 9 + dy * 3 + dx];
+      }
+  } else
   for (auto& s : c.in) {
     for (int ch = 0; ch < s.c; ++ch, ++ci)
       for (int tap = 0; tap < taps; ++tap)
@@ -994,7 +1056,7 @@ static int run_conv(pf_bgnet* net, const Arena& a, int ci, cudaStream_t st) {
   fill_conv_launch(net, a, c, &L);
   if (head) L.cout_store = 16;
   const bool sp = net->precision == 1;
-  return launch_conv_simt(L, c.ksize, c.stride, sp, sp && !head, st);
+  return launch_conv_simt(L, c.ksize, c.exec_stride(), sp, sp && !head, st);
 }
 
 extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* depth_dev,
@@ -1179,10 +1241,15 @@ extern "C" int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_d
   const bool head = i == net->final_conv;
   const bool split = net->precision == 1;
   const bool split_out = split && !head;
-  const int Ho = (H + c.stride - 1) / c.stride, Wo = (W + c.stride - 1) / c.stride;
-  const int cs_out = head ? 16 : padc(c.cout);
-  const size_t in_elems = (size_t)b * H * W * c.kpad, out_elems = (size_t)b * Ho * Wo * cs_out;
-  const size_t esz_in = split ? 2 : 4, esz_out = split_out ? 2 : 4;
+  const bool s2i = c.s2d_in, s2o = c.s2d_out;                 // only set with split storage
+  PF_REQUIRE(!(s2i || s2o) || (H % 2 == 0 && W % 2 == 0), PF_EINVAL, "pf_bgnet_debug_conv: even H, W required");
+  const int es = c.exec_stride();
+  const int He = s2i ? H / 2 : H, We = s2i ? W / 2 : W;       // input extent as the kernel sees it
+  const int Ho = (He + es - 1) / es, Wo = (We + es - 1) / es; // conv output extent
+  const int cs_out = head ? 16 : (s2o ? 128 : padc(c.cout));
+  const size_t in_elems = (size_t)b * He * We * c.kpad;
+  const size_t out_elems = s2o ? (size_t)b * (Ho / 2) * (Wo / 2) * 128 : (size_t)b * Ho * Wo * cs_out;
+  const size_t esz_in = split ? 2 : 4;
   char *xin = nullptr, *xin_lo = nullptr, *yout = nullptr, *yout_lo = nullptr;
   float* xpk = nullptr;
   PF_CHECK_CUDA(cudaMalloc(&xin, in_elems * esz_in));
@@ -1190,9 +1257,13 @@ extern "C" int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_d
   PF_CHECK_CUDA(cudaMalloc(&xpk, (size_t)b * H * W * c.kpad * 4));
   PF_CHECK_CUDA(cudaMalloc(&yout, out_elems * 4));
   PF_CHECK_CUDA(cudaMalloc(&yout_lo, out_elems * 2));
-  // NCHW -> NCHW with each input slice moved to its padded channel position -> NHWC (kpad channels)
-  PF_CHECK_CUDA(cudaMemsetAsync(xpk, 0, (size_t)b * H * W * c.kpad * 4, st));
-  {
+  if (s2i) {
+    nchw_to_s2d_kernel<<<grid_for(in_elems, 256), 256, 0, st>>>(x_nchw_dev, reinterpret_cast<unsigned short*>(xin),
+                                                              reinterpret_cast<unsigned short*>(xin_lo), b, c.cin, H, W);
+    PF_CHECK_CUDA(cudaGetLastError());
+  } else {
+    // NCHW -> NCHW with each input slice moved to its padded channel position -> NHWC (kpad channels)
+    PF_CHECK_CUDA(cudaMemsetAsync(xpk, 0, (size_t)b * H * W * c.kpad * 4, st));
     int src = 0, dst = 0;
     for (auto& s : c.in) {
       PF_CHECK_CUDA(cudaMemcpy2DAsync(xpk + (size_t)dst * H * W, (size_t)c.kpad * H * W * 4,
@@ -1204,26 +1275,26 @@ extern "C" int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_d
     PF_CHECK_CUDA(cudaGetLastError());
   }
   int rc = 0;
-  const bool use_tc = split && !net->force_simt && c.stride == 1;
+  const bool use_tc = split && !net->force_simt && es == 1;
   CUtensorMap* maps_dev = nullptr;
   if (use_tc) {
     TcIo io;
     int dst = 0;
     for (size_t s = 0; s < c.in.size(); ++s) {
       io.in_hi[s] = xin + (size_t)dst * 2; io.in_lo[s] = xin_lo + (size_t)dst * 2;
-      io.in_cs[s] = c.kpad; io.in_img[s] = (size_t)H * W * c.kpad;
+      io.in_cs[s] = c.kpad; io.in_img[s] = (size_t)He * We * c.kpad;
       dst += c.in[s].cpad();
     }
-    io.Hin = H; io.Win = W; io.Hout = Ho; io.Wout = Wo; io.b = b;
+    io.Hin = He; io.Win = We; io.Hout = Ho; io.Wout = Wo; io.b = b;
     io.out_hi = head ? nullptr : yout; io.out_lo = head ? nullptr : yout_lo;
     io.out_f32 = head ? reinterpret_cast<float*>(yout) : nullptr;
-    io.out_cs = cs_out; io.out_img = (size_t)Ho * Wo * cs_out;
+    io.out_cs = cs_out; io.out_img = out_elems / b;
     std::vector<CUtensorMap> maps;
     TcLayer L;
     HaloLayer HL;
     int nblocks; size_t smem;
     int kind = 2;
-    rc = net->no_halo ? 1 : build_halo_layer(net, i, io, &maps, &HL, &nblocks, &smem);
+    rc = (net->no_halo && !s2i && !s2o) ? 1 : build_halo_layer(net, i, io, &maps, &HL, &nblocks, &smem);
     if (rc == 1) { kind = 1; rc = build_tc_layer(net, i, io, &maps, &L, &nblocks, &smem); }
     if (rc == 0) {
       PF_CHECK_CUDA(cudaMalloc(&maps_dev, maps.size() * sizeof(CUtensorMap)));
@@ -1256,17 +1327,24 @@ extern "C" int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_d
     for (int s = 0; s < L.nseg; ++s) {
       L.segs[s].base = xin + (size_t)dst * esz_in; L.segs[s].base_lo = xin_lo + (size_t)dst * 2;
       L.segs[s].cstride = c.kpad; L.segs[s].cpad = c.in[s].cpad();
-      L.in_img_stride[s] = (size_t)H * W * c.kpad;
+      L.in_img_stride[s] = (size_t)He * We * c.kpad;
       dst += c.in[s].cpad();
     }
-    L.b = b; L.Hin = H; L.Win = W; L.Hout = Ho; L.Wout = Wo;
-    L.out = yout; L.out_lo = yout_lo; L.out_cstride = cs_out; L.out_img_stride = (size_t)Ho * Wo * cs_out;
-    L.w = c.w_dev; L.bias = c.bias_dev; L.kpad = c.kpad; L.coutpad = c.coutpad; L.cout_store = cs_out; L.relu = c.relu ? 1 : 0;
-    rc = launch_conv_simt(L, c.ksize, c.stride, split, split_out, st);
+    L.b = b; L.Hin = He; L.Win = We; L.Hout = Ho; L.Wout = Wo;
+    L.out = yout; L.out_lo = yout_lo; L.out_cstride = cs_out; L.out_img_stride = out_elems / b;
+    L.w = c.w_dev; L.bias = c.bias_dev; L.kpad = c.kpad; L.coutpad = c.coutpad; L.relu = c.relu ? 1 : 0;
+    L.cout_store = s2o ? 32 : cs_out;
+    L.s2d_block = s2o ? 32 : 0;
+    rc = launch_conv_simt(L, c.ksize, es, split, split_out, st);
   }
   if (rc == 0) {
     const size_t total = (size_t)b * c.cout * Ho * Wo;
-    nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, st>>>(yout, yout_lo, split_out ? 1 : 0, y_nchw_dev, b, c.cout, Ho, Wo, cs_out);
+    if (s2o)
+      s2d_to_nchw_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<unsigned short*>(yout),
+                                                             reinterpret_cast<unsigned short*>(yout_lo), y_nchw_dev, b,
+                                                             c.cout, Ho, Wo);
+    else
+      nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, st>>>(yout, yout_lo, split_out ? 1 : 0, y_nchw_dev, b, c.cout, Ho, Wo, cs_out);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("pf_bgnet_debug_conv: %s", cudaGetErrorString(e)); rc = (int)e; }
   }

@@ -35,6 +35,11 @@ struct ConvDesc {
   float* w_dev = nullptr;
   float* bias_dev = nullptr;
   bool loaded = false;
+  // tensor-core storage only: base.1 writes its output space-to-depth (4 phase blocks of 32 channels at
+  // half its resolution) so that base.2, the only 3x3 STRIDE-2 ConvLayer besides the first, runs as a
+  // stride-1 conv with 4 active taps over that tensor on the tcgen05 halo kernel.
+  bool s2d_out = false, s2d_in = false;
+  int exec_stride() const { return s2d_in ? 1 : stride; }
   std::vector<float> w_host;     // folded, packed like w_dev (kept for re-packing by the tensor-core path)
   std::vector<float> bias_host;
 };
@@ -67,8 +72,9 @@ struct ConvLaunch {
   size_t out_img_stride;
   const float* w;
   const float* bias;
-  int kpad, coutpad, cout_store; // cout_store = channels written (cout padded to 8)
+  int kpad, coutpad, cout_store; // cout_store = channels written (cout padded to 16)
   int relu;
+  int s2d_block;                 // > 0: write pixel (y,x) to (y/2, x/2), channel block ((y&1)*2+(x&1)) * s2d_block
 };
 
 // split_in / split_out: activations stored as bf16 (hi, lo) planes with x = hi + lo (tensor-core path storage)

@@ -41,6 +41,59 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 }  // namespace
 
+// All MMAs of one staged activation chunk: TAPS filter taps x (W/16) K atoms x 2 MMAs.  Fully unrolled
+// with W / TAPS as template parameters so that every descriptor offset is an immediate: the issue rate
+// of these small-N MMAs is bound by the uniform-datapath instructions between them, not by the tensor pipe.
+struct ChunkIssue {
+  uint32_t d, idesc1, idesc2, el;
+  uint32_t sa, a_tile;          // A stage: hi plane at sa, lo plane at sa + a_tile
+  int nk, tap_mask;
+  // weights: resident -> walk `woff` from smem_base; streamed -> B ring
+  int resident;
+  uint32_t smem_base, pair_step;          // resident: bytes between consecutive taps' [hi;lo] tiles
+  uint32_t b_base, b_tile, bar_full_b0, bar_empty_b0;
+  int SB;
+};
+
+template <int W, int TAPS, bool FIRST>   // FIRST: first chunk of a tile -> its first MMA overwrites the accumulator
+__device__ __forceinline__ void issue_chunk(const ChunkIssue& c, uint32_t& woff, int& ib) {
+  constexpr int HX = TAPS == 9 ? 10 : 8;
+  constexpr uint32_t RP = 2u * W;
+  constexpr uint32_t LAY = W == 64 ? 2u : (W == 32 ? 4u : 6u);
+  constexpr uint32_t A_HI = ((HX * RP) >> 4) | (1u << 14) | (LAY << 29);   // SBO | version | swizzle (upper descriptor word)
+  constexpr uint32_t B_HI = ((8u * RP) >> 4) | (1u << 14) | (LAY << 29);
+  const uint32_t a_hi_lo = ((c.sa & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t a_lo_lo = (((c.sa + c.a_tile) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+  for (int tap = 0; tap < TAPS; ++tap) {
+    if (!((c.tap_mask >> tap) & 1)) continue;
+    constexpr int dummy = 0; (void)dummy;
+    const uint32_t shift = (uint32_t)(((tap / 3) * HX + (tap % 3)) * (int)(RP >> 4));   // immediate after unrolling
+    uint32_t sb;
+    int sbi = 0;
+    if (c.resident) {
+      sb = c.smem_base + woff;
+      woff += c.pair_step;
+    } else {
+      sbi = ib % c.SB;
+      mbar_wait(c.bar_full_b0 + 8u * sbi, (ib / c.SB) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      sb = c.b_base + sbi * c.b_tile;
+      ++ib;
+    }
+    const uint32_t b_lo = ((sb & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+    for (int ka = 0; ka < W / 16; ++ka) {
+      if (ka < c.nk) {
+        // tap 0 is active in every tap mask, so (tap 0, atom 0) of the first chunk is the tile's first MMA
+        umma_bf16_w(c.d, a_hi_lo + shift + 2 * ka, A_HI, b_lo + 2 * ka, B_HI, c.idesc2, (FIRST && tap == 0 && ka == 0) ? 0u : 1u, c.el);
+        umma_bf16_w(c.d, a_lo_lo + shift + 2 * ka, A_HI, b_lo + 2 * ka, B_HI, c.idesc1, 1u, c.el);
+      }
+    }
+    if (!c.resident) umma_commit_p(c.bar_empty_b0 + 8u * sbi, c.el);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxB + 5];
@@ -103,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
           const uint32_t bt = (uint32_t)ntile * 2u * w;            // hi rows, lo rows directly behind them
           for (int c0 = 0; c0 < cpad; c0 += w)
             for (int tap = 0; tap < NT; ++tap) {
+              if (!((L.tap_mask >> tap) & 1)) continue;
               const int koff = L.seg_koff[s] + tap * cpad + c0;
               tma_load_2d_p(smem_base + off, wm, wbar, koff, n0, el);
               tma_load_2d_p(smem_base + off + bt, wm + 1, wbar, koff, n0, el);
@@ -130,7 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
             tma_load_4d_p(sa, am, full_a(st), c0, x0 - org, y0 - org, img, el);
             tma_load_4d_p(sa + a_tile, am + 1, full_a(st), c0, x0 - org, y0 - org, img, el);
             if (!L.resident) {
-              for (int tap = 0; tap < NT; ++tap, ++ib) {
+              for (int tap = 0; tap < NT; ++tap) {
+                if (!((L.tap_mask >> tap) & 1)) continue;
                 const int sb = ib % SB;
                 mbar_wait(empty_b(sb), ((ib / SB) & 1) ^ 1);
                 const uint32_t sbp = b_base + sb * b_tile;
@@ -138,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
                 const int koff = L.seg_koff[s] + tap * cpad + c0;
                 tma_load_2d_p(sbp, wm, full_b(sb), koff, n0, el);
                 tma_load_2d_p(sbp + b_tx, wm + 1, full_b(sb), koff, n0, el);
+                ++ib;
               }
             }
           }
@@ -168,44 +224,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
         bool first = true;
         for (int s = 0; s < L.nseg; ++s) {
           const int cpad = L.seg_cpad[s], w = L.seg_w[s];
-          const uint32_t rp = 2u * w, lay = layout_of(w);
-          const uint32_t bt = (uint32_t)ntile * rp;
+          const uint32_t bt = (uint32_t)ntile * 2u * w;
           for (int c0 = 0; c0 < cpad; c0 += w, ++ia) {
             const int st = ia % SA;
             mbar_wait(full_a(st), (ia / SA) & 1);
             if (dbg && el && ia == 0) L.dbg_ts[3] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = a_base + st * 2 * a_tile;
-            const int nk = min(w, cpad - c0) >> 4;
-            // descriptors are linear in the start address: build the chunk's base descriptors once,
-            // then every (tap, k-atom) is one 64-bit add (the MMA issuer is a single thread).
-            const uint64_t a_hi0 = desc_kmajor(sa, HX * rp, lay);
-            const uint64_t a_lo0 = desc_kmajor(sa + a_tile, HX * rp, lay);
-            const uint32_t tap_step = rp >> 4;                   // one pixel row, in 16-byte units
-            for (int tap = 0; tap < NT; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              const uint64_t shift = (uint64_t)((dy * HX + dx) * tap_step);
-              uint32_t sb_hi;
-              int sbi = 0;
-              if (L.resident) {
-                sb_hi = smem_base + woff;
-                woff += align1k(2 * bt);
-              } else {
-                sbi = ib % SB;
-                mbar_wait(full_b(sbi), (ib / SB) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                sb_hi = b_base + sbi * b_tile;
-                ++ib;
-              }
-              const uint64_t b0 = desc_kmajor(sb_hi, 8 * rp, lay);
-#pragma unroll 4
-              for (int ka = 0; ka < nk; ++ka) {
-                const uint64_t ko = (uint64_t)(ka * 2);          // 32 bytes per k-atom
-                umma_bf16_p(d, a_hi0 + shift + ko, b0 + ko, idesc2, first ? 0u : 1u, el);
-                first = false;
-                umma_bf16_p(d, a_lo0 + shift + ko, b0 + ko, idesc1, 1u, el);
-              }
-              if (!L.resident) umma_commit_p(empty_b(sbi), el);
+            ChunkIssue ci;
+            ci.d = d; ci.idesc1 = idesc1; ci.idesc2 = idesc2; ci.el = el;
+            ci.sa = sa; ci.a_tile = a_tile;
+            ci.nk = min(w, cpad - c0) >> 4; ci.tap_mask = L.tap_mask;
+            ci.resident = L.resident; ci.smem_base = smem_base; ci.pair_step = align1k(2 * bt);
+            ci.b_base = b_base; ci.b_tile = b_tile; ci.bar_full_b0 = full_b(0); ci.bar_empty_b0 = empty_b(0); ci.SB = SB;
+            const bool fc = first;
+            first = false;
+            if (NT == 9) {
+              if (w == 64) { if (fc) issue_chunk<64, 9, true>(ci, woff, ib); else issue_chunk<64, 9, false>(ci, woff, ib); }
+              else if (w == 32) { if (fc) issue_chunk<32, 9, true>(ci, woff, ib); else issue_chunk<32, 9, false>(ci, woff, ib); }
+              else { if (fc) issue_chunk<16, 9, true>(ci, woff, ib); else issue_chunk<16, 9, false>(ci, woff, ib); }
+            } else {
+              if (w == 64) { if (fc) issue_chunk<64, 1, true>(ci, woff, ib); else issue_chunk<64, 1, false>(ci, woff, ib); }
+              else if (w == 32) { if (fc) issue_chunk<32, 1, true>(ci, woff, ib); else issue_chunk<32, 1, false>(ci, woff, ib); }
+              else { if (fc) issue_chunk<16, 1, true>(ci, woff, ib); else issue_chunk<16, 1, false>(ci, woff, ib); }
             }
             umma_commit_p(empty_a(st), el);
           }
@@ -231,7 +272,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
       mbar_wait(tmem_full(acc), (tc_ >> 1) & 1);
       if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const size_t pix = (size_t)img * L.out_img_stride + ((size_t)oy * L.Wout + ox) * L.out_cs;
+      const size_t pix = L.s2d_block
+                             ? (size_t)img * L.out_img_stride + ((size_t)(oy >> 1) * (L.Wout >> 1) + (ox >> 1)) * L.out_cs +
+                                   (size_t)((oy & 1) * 2 + (ox & 1)) * L.s2d_block
+                             : (size_t)img * L.out_img_stride + ((size_t)oy * L.Wout + ox) * L.out_cs;
       for (int c = 0; c < ntile; c += 16) {
         const int n = n0 + c;
         if (n >= L.cout_store) break;
@@ -340,8 +384,9 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
     if (w > wmax) wmax = w;
     const int nchunks = (L->seg_cpad[s] + w - 1) / w;
     const size_t bt = align_up((size_t)2 * L->ntile * 2 * w, 1024);   // [hi rows ; lo rows] of one tap
-    w_total += (size_t)nchunks * L->taps * bt;
-    w_tx += (size_t)nchunks * L->taps * 2 * (size_t)L->ntile * 2 * w;
+    const int nact = __builtin_popcount((unsigned)L->tap_mask & ((1u << L->taps) - 1u));
+    w_total += (size_t)nchunks * nact * bt;
+    w_tx += (size_t)nchunks * nact * 2 * (size_t)L->ntile * 2 * w;
   }
   const size_t a_tile = align_up((size_t)L->hx * L->hy * 2 * wmax, 1024);
   const size_t b_tile = align_up((size_t)2 * L->ntile * 2 * wmax, 1024);

@@ -121,7 +121,10 @@ __global__ void __launch_bounds__(16 * NT / 4) conv_simt_kernel(const ConvLaunch
   const float4 bv = *reinterpret_cast<const float4*>(L.bias + n);
   const int oy = oy0 + py;
   if (oy >= L.Hout) return;
-  const size_t orow = (size_t)img * L.out_img_stride + (size_t)oy * L.Wout * L.out_cstride + n;
+  const size_t orow = L.s2d_block
+                          ? (size_t)img * L.out_img_stride + (size_t)(oy >> 1) * (L.Wout >> 1) * L.out_cstride +
+                                (size_t)((oy & 1) * 2) * L.s2d_block + n
+                          : (size_t)img * L.out_img_stride + (size_t)oy * L.Wout * L.out_cstride + n;
 #pragma unroll
   for (int i = 0; i < PXT; ++i) {
     const int ox = ox0 + px0 + i;
@@ -130,7 +133,8 @@ __global__ void __launch_bounds__(16 * NT / 4) conv_simt_kernel(const ConvLaunch
     if (L.relu) {
       r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
     }
-    const size_t o = orow + (size_t)ox * L.out_cstride;
+    const size_t o = L.s2d_block ? orow + (size_t)(ox >> 1) * L.out_cstride + (size_t)(ox & 1) * L.s2d_block
+                                 : orow + (size_t)ox * L.out_cstride;
     if (!SPLIT_OUT) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(L.out) + o) = r;
     } else {

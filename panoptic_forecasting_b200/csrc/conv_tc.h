@@ -38,6 +38,8 @@ struct HaloLayer {
   int w_map[3];             // weight tensor maps (hi; lo = +1) for chunk widths 16 / 32 / 64
   int Hout, Wout, tiles_x, tiles_y, batch;
   int taps, hx, hy;         // 9 taps / 10 x 18 box (3x3) or 1 tap / 8 x 16 box (1x1)
+  int tap_mask;             // active taps (bit dy*3+dx); 0x1FF normally, 0x1B for the space-to-depth stride-2 conv
+  int s2d_block;            // > 0: space-to-depth output (see ConvDesc::s2d_out)
   int ntile, tmem_cols, stages_a, stages_b;
   uint32_t a_tile_bytes, b_tile_bytes;
   int resident;             // weights stay in shared memory for the whole kernel

@@ -21,6 +21,17 @@ __device__ __forceinline__ void split_store4(const float4& r, uint2* h, uint2* l
   l->x = l0 | (l1 << 16); l->y = l2 | (l3 << 16);
 }
 
+// two values at once: one packed cvt.rn.bf16x2.f32 per plane
+__device__ __forceinline__ void split2(float a, float b, unsigned* hi, unsigned* lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const unsigned hu = *reinterpret_cast<const unsigned*>(&h);
+  const float ra = a - __uint_as_float(hu << 16);
+  const float rb = b - __uint_as_float(hu & 0xFFFF0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  *hi = hu;
+  *lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
 __device__ __forceinline__ float bf16lo(unsigned packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi(unsigned packed) { return __uint_as_float(packed & 0xFFFF0000u); }
 

@@ -83,6 +83,15 @@ static __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 
+static __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+static __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- single-lane issue from warp-uniform code ------------------------------------------------
 // tcgen05.mma / tcgen05.commit / TMA take their operands in UNIFORM registers.  If the issuing
 // code sits in a divergent `if (lane == 0)` region, ptxas cannot prove uniformity and wraps every
@@ -128,6 +137,20 @@ static __device__ __forceinline__ void umma_bf16_p(uint32_t tmem_d, uint64_t da,
       "setp.ne.b32 q, %5, 0;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(pred)
+      : "memory");
+}
+// descriptors passed as (lo, hi) 32-bit words: only the low word (start address) changes between MMAs,
+// so the issuing warp's uniform datapath does one 32-bit add per operand instead of 64-bit carry chains.
+static __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                    uint32_t idesc, uint32_t acc, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(pred)
       : "memory");
 }
 static __device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t pred) {
