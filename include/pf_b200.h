@@ -138,6 +138,7 @@ int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* de
 /* number of kernel launches one pf_bgnet_forward enqueues (for bench.py's gpu_launches) */
 int pf_bgnet_launches_per_forward(const pf_bgnet_t* net);
 int pf_zsplat_launches_per_forward(void);
+int pf_zsplat_launches_for(int b, int t, int H, int W);   /* per-frame mode: point kernels run per L2-sized group */
 
 /* Per-step device timing (CUDA events recorded on the caller's stream around every step of the
  * next `max_iters` forwards); pf_bgnet_read_profile synchronises on the last event and returns

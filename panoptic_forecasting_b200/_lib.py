@@ -29,6 +29,7 @@ SIGNATURES = {
     "pf_zsplat_forward_frames": (_i, [_vp] * 8 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
     "pf_zsplat_forward_host": (_i, [_vp] * 8 + [_i] * 5 + [_vp] * 3),
     "pf_zsplat_launches_per_forward": (_i, []),
+    "pf_zsplat_launches_for": (_i, [_i, _i, _i, _i]),
     "pf_depth_disk_hop": (_i, [_vp, _vp, _vp, _sz, _f, _f, _vp]),
     "pf_bgnet_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
     "pf_bgnet_destroy": (None, [_vp]),

@@ -142,6 +142,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_smem;
   if (dbg && threadIdx.x == 0) L.dbg_ts[1] = clock64();
+  // Programmatic dependent launch: let the next layer's CTAs start their prologue (barriers, TMEM,
+  // weight loads -- nothing that depends on this layer) on idle SMs right away ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform loops, one elected lane issues) =====
@@ -164,6 +167,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
             }
         }
       }
+      // ... and do not read the previous layer's activations before it has completed and flushed.
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       int ia = 0, ib = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int img = t / tiles_per_img;
@@ -424,8 +429,19 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   int gx = kNumSMs / nblocks;
   if (gx < 1) gx = 1;
   if (gx > total_tiles) gx = total_tiles;
-  conv_halo_kernel<<<dim3(gx, nblocks), kThreads, smem_bytes, st>>>(L, maps_dev);
-  PF_CHECK_CUDA(cudaGetLastError());
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("PF_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, nblocks);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr_pdl[1];
+  attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr_pdl;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel, L, maps_dev));
   return 0;
 }
 
