@@ -243,9 +243,8 @@ def main():
     for i in range(K):
         inp = dev_sets[i % args.nsets]
         ev_a[i][0].record()
-        seg, depth = pipe.warp(inp)
+        seg, d, m = pipe.warp(inp, fuse_hop=True)          # disk hop fused into the resolve kernel
         ev_a[i][1].record()
-        d, m = pipe.decode_depth(depth)
         ev_b[i][0].record()
         out = bg.predict({"seg": seg, "depth": d, "depth_mask": m}, {})
         ev_b[i][1].record()
@@ -327,7 +326,7 @@ def main():
     e2e_fps = world * B * Ke / (float(t.item()) / 1e3)
     clocks = sampler.stop() if sampler else None
 
-    launches_per_step = L.pf_zsplat_launches_for(B, T, H, W) + 1 + L.pf_bgnet_launches_per_forward(bg._net)
+    launches_per_step = L.pf_zsplat_launches_for(B, T, H, W) + L.pf_bgnet_launches_per_forward(bg._net)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

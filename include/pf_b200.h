@@ -75,6 +75,17 @@ int pf_zsplat_forward_frames(const float* depth_dev, const uint8_t* mask_dev, co
                              uint8_t* out_seg_dev, float* out_depth_dev, int64_t* out_coords_dev,
                              void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Per-frame mode with the disk hop fused into the resolve kernel: out_depth_dev receives the depth as
+ * BGDataset would decode it from the exporter's uint16 PNG (see pf_depth_disk_hop) and out_mask_dev
+ * (u8 [b,t,H,W]) its validity mask.  payload is 1. */
+int pf_zsplat_forward_frames_hop(const float* depth_dev, const uint8_t* mask_dev, const uint8_t* seg_dev,
+                                 const float* K_dev, const float* Kinv_dev,
+                                 const float* E_dev, const float* Einv_dev, const float* T_dev,
+                                 int b, int t, int H, int W, const uint8_t* lut_dev,
+                                 uint8_t* out_seg_dev, float* out_depth_dev, uint8_t* out_mask_dev,
+                                 float min_depth, float max_depth,
+                                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Same, with HOST buffers: copies inputs to the device, runs, copies seg/depth back and
  * synchronises the stream.  This is the end-to-end call bench.py times as `e2e`. */
 int pf_zsplat_forward_host(const float* depth, const uint8_t* mask, const uint8_t* seg,

@@ -23,10 +23,11 @@ class BGForecastPipeline:
         self._lib = _lib.lib()
         self._ws = None
 
-    def warp(self, inputs):
+    def warp(self, inputs, fuse_hop=False):
         """All t frames reprojected into the target frame, each in its own z-buffer
         (== t reference PCTransformModel.predict calls with only_this_ind = 0..t-1).
-        Returns (seg u8 [b,t,H,W], depth f32 [b,t,H,W])."""
+        Returns (seg u8 [b,t,H,W], depth f32 [b,t,H,W]); with fuse_hop=True the depth is already
+        disk-hop decoded and a third value, the u8 validity mask, is returned."""
         depth = inputs['depth']
         if not depth.is_cuda:
             raise _lib.PFError("BGForecastPipeline needs CUDA tensors (no CPU fallback)")
@@ -50,6 +51,17 @@ class BGForecastPipeline:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out_seg = torch.empty((b, t, H, W), dtype=torch.uint8, device=dev)
         out_depth = torch.empty((b, t, H, W), dtype=torch.float32, device=dev)
+        if fuse_hop:
+            out_mask = torch.empty((b, t, H, W), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                rc = self._lib.pf_zsplat_forward_frames_hop(
+                    depth_c.data_ptr(), mask_c.data_ptr(), seg_c.data_ptr(), K.data_ptr(), Kinv.data_ptr(),
+                    E.data_ptr(), Einv.data_ptr(), T.data_ptr(), b, t, H, W, None,
+                    out_seg.data_ptr(), out_depth.data_ptr(), out_mask.data_ptr(), float(self.min_depth),
+                    float(self.max_depth), self._ws.data_ptr(), self._ws.numel(), stream)
+            _lib.check(rc, "pf_zsplat_forward_frames_hop")
+            return out_seg, out_depth, out_mask
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = self._lib.pf_zsplat_forward_frames(
@@ -79,8 +91,11 @@ class BGForecastPipeline:
     def forecast(self, inputs):
         """inputs: the PCTransformModel input dict (pc_transform_model.py:27-32).
         Returns the BGModel.predict dict plus 'warped_seg' / 'warped_depth' / 'warped_mask'."""
-        seg, depth = self.warp(inputs)
-        d, m = self.decode_depth(depth)
+        if self.emulate_disk_hop:
+            seg, d, m = self.warp(inputs, fuse_hop=True)      # hop fused into the resolve kernel
+        else:
+            seg, depth = self.warp(inputs)
+            d, m = self.decode_depth(depth)
         out = self.bg.predict({'seg': seg, 'depth': d, 'depth_mask': m}, {})
         out['warped_seg'], out['warped_depth'], out['warped_mask'] = seg, d, m
         return out

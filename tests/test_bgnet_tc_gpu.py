@@ -69,3 +69,10 @@ def test_whole_net_tcgen05(pf_lib, bg_shapes, shape, final):
     out32 = gpu_model(sd, final, precision="fp32").predict(cu, {})
     scale = out32["logits"].abs().max().item()
     assert (out["logits"] - out32["logits"]).abs().max().item() <= 3e-4 * scale
+
+
+def test_every_conv_layer_tcgen05_per_tap_kernel(pf_lib, bg_shapes, monkeypatch):
+    """PF_TC_NO_HALO=1: the one-TMA-box-per-tap tcgen05 kernel (conv_tc.cu) stays correct."""
+    monkeypatch.delenv("PF_TC_FORCE_SIMT", raising=False)
+    monkeypatch.setenv("PF_TC_NO_HALO", "1")
+    layer_sweep(pf_lib, bg_shapes, 1e-4)

@@ -73,6 +73,8 @@ def test_edge_cases_bit_exact(pf_lib):
     c = dict(base); T = base["target_T"].copy(); T[0, :, 0, 3] = 40.0; c["target_T"] = T; cases.append(c)  # off-image -> clamp
     c = dict(base); m = np.ones((1, 2, H, W), bool); m[0, :, ::2] = False; c["depth_mask"] = m; cases.append(c)
     c = dict(base); d = base["depth"].copy(); d[0, 1] = 4.0; c["depth"] = d; cases.append(c)  # frame 1 nearer
+    c = dict(base); E = base["extrinsics"].copy(); E[0, 3] = [0.0, 0.0, 0.01, 1.0]; c["extrinsics"] = E   # projective last row:
+    c["extrinsics_inv"] = np.linalg.inv(E).astype(np.float32); c["intrinsics_inv"] = eye(3); cases.append(c)  # w != 1 path
     for c in cases:
         for ind in (None, 1):
             assert_same(run_gpu(c, ind), pc_transform_oracle.predict(c, only_this_ind=ind))
