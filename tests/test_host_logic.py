@@ -75,3 +75,20 @@ def test_synthetic_inputs_are_seeded_and_shaped():
     assert 0.05 < frac < 0.4
     T = a["target_T"][0, 0].numpy()
     assert abs(np.linalg.det(T[:3, :3]) - 1) < 1e-4 and T[0, 3] < -5.0    # ~15 steps of ~0.6 m forward
+
+
+def test_ego_transforms_match_reference_formulas():
+    """ego.target_T_from_odometry == product of the reference's unicycle steps (data_utils.py:117-165,
+    restated in synthetic.vehicle_now_T_prev with np.linalg.inv as the reference does)."""
+    from panoptic_forecasting_b200 import ego
+    rng = np.random.default_rng(3)
+    speed = rng.uniform(0, 20, size=(4, 15))
+    yaw = rng.normal(0, 0.05, size=(4, 15))
+    yaw[0, :3] = 0.0001            # straight-line branch
+    dt = rng.uniform(0.05, 0.07, size=(4, 15))
+    got = ego.target_T_from_odometry(torch.from_numpy(speed), torch.from_numpy(yaw), torch.from_numpy(dt)).numpy()
+    for b in range(4):
+        T = np.eye(4)
+        for k in range(15):
+            T = synthetic.vehicle_now_T_prev(speed[b, k], yaw[b, k], dt[b, k]) @ T
+        assert np.abs(got[b] - T.astype(np.float32)).max() <= 1e-5
