@@ -293,9 +293,22 @@ def main():
             "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
             "ms_per_step": net_ms, "timed_steps": K, "peak_source": peaks["source"],
             "note": "algorithmic 75.32 GFLOP/frame; the split-bf16 scheme executes 2 tensor-core MMAs per algorithmic MAC"}
+    # DRAM traffic per step from the committed ncu capture of this same command (profiles/, batch 8 only)
+    traffic_b = traffic_a = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_v6_traffic_per_step.json")))
+        if tr.get("batch") == B:
+            ks = tr["per_step"]
+            tot = lambda pred: sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in ks.items() if pred(k))
+            traffic_b = tot(lambda k: not k.startswith("zsplat") and "zsplat" not in k)
+            traffic_a = tot(lambda k: "zsplat" in k)
+    except Exception:
+        pass
+    roof["traffic"] = traffic_b
+    roof["traffic_note"] = "bytes per step (all Stage B kernels), ncu dram__bytes_read+write, profiles/r1_v6_traffic_per_step.json"
     a_gbs = STAGE_A_BYTES_PER_FRAME * B / (warp_ms * 1e-3) / 1e9
     roof_a = {"bound": "hbm", "kernel": "pf_zsplat_forward_frames (points + resolve)", "achieved": a_gbs,
-              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a_gbs / peaks["hbm_gbs"], "traffic": None,
+              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a_gbs / peaks["hbm_gbs"], "traffic": traffic_a,
               "ms_per_step": warp_ms}
 
     # ---- timed region 2: end to end through the public API from pinned host buffers (`e2e`):
