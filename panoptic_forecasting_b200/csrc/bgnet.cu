@@ -15,6 +15,7 @@
 #include "bgnet.h"
 #include "conv_tc.h"
 #include "split_bf16.cuh"
+#include "tc_common.cuh"
 
 namespace pf {
 
@@ -72,6 +73,9 @@ struct pf_bgnet {
   // first conv (labels -> 16 ch) tables: lut[tap][frame][class+1][16], wd[tap][frame][16], bias[16]
   float* first_tab_dev = nullptr;
   size_t first_tab_floats = 0;
+  void* first_maps_dev = nullptr;            // TMA tensor maps of the caller's labels / depth / mask tensors
+  const void *fm_labels = nullptr, *fm_depth = nullptr, *fm_mask = nullptr;
+  int fm_b = 0, fm_H = 0, fm_W = 0;
   int launches = 0;
   // tensor-core path (precision 1): packed split-bf16 weights live in ConvDesc-indexed arrays; the
   // TMA tensor maps depend on the arena address and shape, so they are cached per (ws, b, H, W).
@@ -258,9 +262,28 @@ static void build_topology(pf_bgnet* net) {
 constexpr int F_TH = 8, F_TW = 32;
 constexpr int F_IH = F_TH * 2 + 1, F_IW = F_TW * 2 + 1;
 
+// depth-plane weights wd[tap][frame][16] and bias[16] of the first conv live in constant memory (uniform
+// operands of FFMA, no shared-memory traffic); refreshed on the stream before every launch (2 KB D2D).
+constexpr int kFirstMaxT = 8;
+__constant__ float c_first_wd[9 * kFirstMaxT * 16 + 16];
+
+// TMA boxes must start on a 16-byte boundary of the innermost (x) dimension: the window's first column
+// ix0 = 64k - 1 is odd, so the depth box starts 3 pixels earlier and the label / mask boxes 15 pixels earlier.
+constexpr int F_DOFF = 3, F_LOFF = 15;
+constexpr int F_DPITCH = 72;     // staged depth row: 72 floats (288 B), columns [ix0 - 3, ix0 + 69)
+constexpr int F_LPITCH = 96;     // staged label / mask row: 96 bytes, columns [ix0 - 15, ix0 + 81)
+constexpr int F_DFRAME = 1248;   // floats per staged depth frame (17 x 72 = 1224, padded: TMA destinations are 128-byte aligned)
+constexpr int F_LFRAME = 1664;   // bytes per staged label / mask frame (17 x 96 = 1632, padded to 128)
+
+struct FirstMaps {
+  alignas(64) CUtensorMap m_depth;   // f32 (W, H, b*t), box 68 x 17 x 1
+  alignas(64) CUtensorMap m_label;   // u8  (W, H, b*t), box 80 x 17 x 1
+  alignas(64) CUtensorMap m_mask;    // u8  (W, H, b*t), box 80 x 17 x 1
+};
+
 struct FirstParams {
-  const uint8_t* labels; const float* depth; const uint8_t* mask;
-  const float* tab;    // lut | wd | bias
+  const FirstMaps* maps;   // device memory (tensor maps of the caller's input tensors)
+  const float* tab;    // lut | wd | bias | lutsum
   void* out;           // NHWC, 16 channels: fp32, or bf16 hi plane
   void* out_lo;        // bf16 lo plane (split storage)
   int split;
@@ -268,90 +291,122 @@ struct FirstParams {
   float mean, std;
 };
 
-__global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(FirstParams p) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+// The input window of a CTA ((2*8+1) x (2*32+1) pixels x t frames of labels, depth, mask) is staged by
+// TMA (3 boxes per frame, image borders zero-filled), then one in-place pass turns it into the two arrays
+// the taps read: the table row index of every pixel and its normalised masked depth.
+__global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParams p) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ __align__(8) uint64_t bar;
   const int lut_floats = 9 * p.t * (p.ncls + 1) * 16;
   const int wd_floats = 9 * p.t * 16;
-  float* lut = reinterpret_cast<float*>(smraw);
-  float* wd = lut + lut_floats;
-  float* bias = wd + wd_floats;
-  float* dn = bias + 16;                                  // [t][F_IH][F_IW]
-  uint8_t* lab = reinterpret_cast<uint8_t*>(dn + p.t * F_IH * F_IW);   // [t][F_IH][F_IW]
+  const int sum_floats = p.t * (p.ncls + 1) * 16;
+  const int tab_floats = lut_floats + wd_floats + 16 + sum_floats;
+  // dynamic smem: [depth/dn: t x 17 x 68 f32][labels: t x 17 x 80 u8][mask: t x 17 x 80 u8][tables]
+  // TMA destinations must be 128-byte aligned: align the dynamic window by hand
+  unsigned char* sm0 = smraw + ((128u - ((uint32_t)__cvta_generic_to_shared(smraw) & 127u)) & 127u);
+  float* dn = reinterpret_cast<float*>(sm0);
+  uint8_t* lab = reinterpret_cast<uint8_t*>(dn + p.t * F_DFRAME);
+  uint8_t* msk = lab + p.t * F_LFRAME;
+  float* lut = reinterpret_cast<float*>(msk + p.t * F_LFRAME);
+  const float* lutsum = lut + lut_floats + wd_floats + 16;
   const int tid = threadIdx.x;
-  for (int i = tid; i < lut_floats + wd_floats + 16; i += blockDim.x) lut[i] = p.tab[i];
   const int tiles_x = (p.Wo + F_TW - 1) / F_TW;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
   const int img = blockIdx.y;
   const int oy0 = ty * F_TH, ox0 = tx * F_TW;
   const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-  const size_t N = (size_t)p.H * p.W;
-  // stage the (2*8+1) x (2*32+1) x t input window; loads are issued four at a time per thread before
-  // any of them is consumed (the kernel is otherwise bound by global-load latency here)
-  const int n_in = p.t * F_IH * F_IW;
-  for (int i0 = tid; i0 < n_in; i0 += 4 * (int)blockDim.x) {
-    uint8_t lv[4], mv[4];
-    float dv[4];
-    bool ok[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * (int)blockDim.x;
-      ok[j] = false;
-      lv[j] = 0; mv[j] = 0; dv[j] = 0.f;
-      if (i < n_in) {
-        const int f = i / (F_IH * F_IW);
-        const int r = i - f * (F_IH * F_IW);
-        const int hy = r / F_IW, hx = r - hy * F_IW;
-        const int iy = iy0 + hy, ix = ix0 + hx;
-        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-          const size_t o = ((size_t)img * p.t + f) * N + (size_t)iy * p.W + ix;
-          ok[j] = true;
-          lv[j] = __ldg(p.labels + o);
-          if (p.use_depth) { dv[j] = __ldg(p.depth + o); mv[j] = __ldg(p.mask + o); }
-        }
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (tid == 0) {
+    tc::mbar_init(bar_a, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)p.t * F_IH * (F_DPITCH * 4 * (p.use_depth ? 1 : 0) + F_LPITCH * (p.use_depth ? 2 : 1));
+    tc::mbar_expect_tx(bar_a, bytes);
+    for (int f = 0; f < p.t; ++f) {
+      const int z = img * p.t + f;
+      // label / mask planes are fetched as 32-bit words starting 15 pixels left of the window
+      const int xw = (ix0 - F_LOFF) >> 2;
+      const int xd = ix0 - F_DOFF;
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(lab + f * F_LFRAME)), "l"(&p.maps->m_label), "r"(bar_a),
+                     "r"(xw), "r"(z * p.H + iy0) : "memory");
+      if (p.use_depth) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(dn + f * F_DFRAME)), "l"(&p.maps->m_depth), "r"(bar_a),
+                       "r"(xd), "r"(z * p.H + iy0) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(msk + f * F_LFRAME)), "l"(&p.maps->m_mask), "r"(bar_a),
+                       "r"(xw), "r"(z * p.H + iy0) : "memory");
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * (int)blockDim.x;
-      if (i >= n_in) break;
-      uint8_t l = (uint8_t)p.ncls;   // zero row: padding or class id >= num_classes
+  }
+  // tables while the boxes are in flight
+  for (int i = tid; i < tab_floats; i += blockDim.x) lut[i] = p.tab[i];
+  __syncthreads();                 // barrier initialised / tables visible
+  tc::mbar_wait(bar_a, 0);
+  // in-place conversion: label -> table row (ncls = zero row for padding and ids >= num_classes),
+  // depth -> (d - mean) / std * mask (bg_model.py:50-51,67-68), 0 outside the image
+  for (int i = tid; i < p.t * F_IH * F_IW; i += blockDim.x) {
+    const int f = i / (F_IH * F_IW);
+    const int r = i - f * (F_IH * F_IW);
+    const int hy = r / F_IW, hx = r - hy * F_IW;
+    const int iy = iy0 + hy, ix = ix0 + hx;
+    const bool inb = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    const int li = f * F_LFRAME + hy * F_LPITCH + hx + F_LOFF, di = f * F_DFRAME + hy * F_DPITCH + hx + F_DOFF;
+    const uint8_t lv = lab[li];
+    lab[li] = (inb && lv < p.ncls) ? lv : (uint8_t)p.ncls;
+    if (p.use_depth) {
       float d = 0.f;
-      if (ok[j]) {
-        if (lv[j] < p.ncls) l = lv[j];
-        if (p.use_depth) {
-          // bg_model.py:50-51,67-68: (d - mean) / std, then * mask
-          const float v = __fdiv_rn(__fadd_rn(dv[j], -p.mean), p.std);
-          d = mv[j] ? v : __fmul_rn(v, 0.0f);
-        }
+      if (inb) {
+        const float v = __fdiv_rn(__fadd_rn(dn[di], -p.mean), p.std);
+        d = msk[li] ? v : __fmul_rn(v, 0.0f);
       }
-      lab[i] = l;
-      dn[i] = d;
+      dn[di] = d;
     }
   }
   __syncthreads();
   const int py = tid / F_TW, px = tid % F_TW;
   float acc[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = bias[j];
+  for (int j = 0; j < 16; ++j) acc[j] = c_first_wd[9 * p.t * 16 + j];
   for (int f = 0; f < p.t; ++f) {
+    const int l0 = f * F_LFRAME + (py * 2) * F_LPITCH + px * 2 + F_LOFF;
+    const int d0 = f * F_DFRAME + (py * 2) * F_DPITCH + px * 2 + F_DOFF;
+    int l[9];
+    float d[9];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const int tap = dy * 3 + dx;
-        const int hi = f * F_IH * F_IW + (py * 2 + dy) * F_IW + px * 2 + dx;
-        const int l = lab[hi];
-        const float d = dn[hi];
-        const float4* row = reinterpret_cast<const float4*>(lut + ((tap * p.t + f) * (p.ncls + 1) + l) * 16);
-        const float4* wr = reinterpret_cast<const float4*>(wd + (tap * p.t + f) * 16);
+        l[dy * 3 + dx] = lab[l0 + dy * F_LPITCH + dx];
+        d[dy * 3 + dx] = p.use_depth ? dn[d0 + dy * F_DPITCH + dx] : 0.f;
+      }
+    // depth planes: 9 taps x 16 FFMA with constant-bank weights
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float* w = c_first_wd + (tap * p.t + f) * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(d[tap], w[j], acc[j]);
+    }
+    // label planes: label maps are piecewise constant, so the 3x3 window of a frame is usually one label:
+    // then the nine table rows collapse into one pre-summed row (4 instead of 36 128-bit shared loads).
+    bool same = true;
+#pragma unroll
+    for (int tap = 1; tap < 9; ++tap) same = same && (l[tap] == l[0]);
+    if (same) {
+      const float4* row = reinterpret_cast<const float4*>(lutsum + (f * (p.ncls + 1) + l[0]) * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = row[q];
+        acc[q * 4 + 0] += a.x; acc[q * 4 + 1] += a.y; acc[q * 4 + 2] += a.z; acc[q * 4 + 3] += a.w;
+      }
+    } else {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float4* row = reinterpret_cast<const float4*>(lut + ((tap * p.t + f) * (p.ncls + 1) + l[tap]) * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 a = row[q];
-          const float4 w = wr[q];
-          acc[q * 4 + 0] = fmaf(d, w.x, acc[q * 4 + 0] + a.x);
-          acc[q * 4 + 1] = fmaf(d, w.y, acc[q * 4 + 1] + a.y);
-          acc[q * 4 + 2] = fmaf(d, w.z, acc[q * 4 + 2] + a.z);
-          acc[q * 4 + 3] = fmaf(d, w.w, acc[q * 4 + 3] + a.w);
+          acc[q * 4 + 0] += a.x; acc[q * 4 + 1] += a.y; acc[q * 4 + 2] += a.z; acc[q * 4 + 3] += a.w;
         }
       }
     }
@@ -366,6 +421,51 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(FirstParams p) {
                              fmaxf(acc[q * 4 + 3], 0.f)),
                  p.split != 0);
   }
+}
+
+// tensor maps of the caller's input tensors for first_conv_kernel (encoded per call: pointers are the caller's)
+static int first_conv_maps(FirstMaps* p, const uint8_t* labels, const float* depth, const uint8_t* mask, int bt, int H,
+                           int W, bool use_depth) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      enc = (EncodeTiledFn)fp;
+  }
+  PF_REQUIRE(enc, PF_ESTATE, "cuTensorMapEncodeTiled not available from the driver");
+  // 2-D maps over (W, H * frames): rows above / below an image belong to the neighbouring frame, the
+  // kernel's in-bounds test discards them (only rows outside the whole tensor are zero-filled by TMA)
+  cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H * bt};
+  cuuint32_t estr[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(W / 4), (cuuint64_t)H * bt};     // bytes viewed as 32-bit words
+    cuuint64_t strides[1] = {(cuuint64_t)W};
+    cuuint32_t box[2] = {(cuuint32_t)(F_LPITCH / 4), (cuuint32_t)F_IH};
+    CUresult r = enc(&p->m_label, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(labels), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PF_REQUIRE(r == CUDA_SUCCESS, PF_EINVAL, "cuTensorMapEncodeTiled(labels) failed: %d", (int)r);
+    if (use_depth) {
+      r = enc(&p->m_mask, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(mask), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      PF_REQUIRE(r == CUDA_SUCCESS, PF_EINVAL, "cuTensorMapEncodeTiled(mask) failed: %d", (int)r);
+    }
+  }
+  if (use_depth) {
+    cuuint64_t strides[1] = {(cuuint64_t)W * 4};
+    cuuint32_t box[2] = {(cuuint32_t)F_DPITCH, (cuuint32_t)F_IH};
+    CUresult r = enc(&p->m_depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(depth), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PF_REQUIRE(r == CUDA_SUCCESS, PF_EINVAL, "cuTensorMapEncodeTiled(depth) failed: %d", (int)r);
+  }
+  return 0;
 }
 
 // AvgPool2d(2,2) (hardnet.py:296) NHWC slice -> NHWC slice, 4 channels per thread.
@@ -996,6 +1096,7 @@ extern "C" void pf_bgnet_destroy(pf_bgnet_t* net) {
   for (auto p : net->wtc_dev) if (p) cudaFree(p);
   if (net->plan.maps_dev) cudaFree(net->plan.maps_dev);
   if (net->first_tab_dev) cudaFree(net->first_tab_dev);
+  if (net->first_maps_dev) cudaFree(net->first_maps_dev);
   for (auto e : net->prof_ev) cudaEventDestroy(e);
   delete net;
 }
@@ -1031,6 +1132,16 @@ static int upload_conv(pf_bgnet* net, int i, const std::vector<double>& wfold /*
             tab[lut_n + (size_t)(tap * t + f) * 16 + o] = (float)wfold[((size_t)o * c.cin + t * C + f) * 9 + tap];
       }
     for (int o = 0; o < c.cout; ++o) tab[lut_n + wd_n + o] = (float)bfold[o];
+    // pre-summed rows for windows with a single label: lutsum[f][cls][o] = sum over the 9 taps
+    tab.resize(lut_n + wd_n + 16 + (size_t)t * (C + 1) * 16, 0.f);
+    for (int f = 0; f < t; ++f)
+      for (int cls = 0; cls < C; ++cls)
+        for (int o = 0; o < c.cout; ++o) {
+          double sacc = 0;
+          for (int tap = 0; tap < 9; ++tap) sacc += wfold[((size_t)o * c.cin + f * C + cls) * 9 + tap];
+          tab[lut_n + wd_n + 16 + ((size_t)f * (C + 1) + cls) * 16 + o] = (float)sacc;
+        }
+    if (net->first_tab_dev) { cudaFree(net->first_tab_dev); net->first_tab_dev = nullptr; }
     if (!net->first_tab_dev) PF_CHECK_CUDA(cudaMalloc(&net->first_tab_dev, tab.size() * sizeof(float)));
     net->first_tab_floats = tab.size();
     PF_CHECK_CUDA(cudaMemcpy(net->first_tab_dev, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1166,11 +1277,32 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
       case STEP_FIRST: {
         const ConvDesc& c = net->convs[s.conv];
         FirstParams p;
-        p.labels = labels_dev; p.depth = depth_dev; p.mask = mask_dev; p.tab = net->first_tab_dev;
+        {
+          PF_REQUIRE(((size_t)labels_dev & 15) == 0 && ((size_t)depth_dev & 15) == 0 && ((size_t)mask_dev & 15) == 0,
+                     PF_EINVAL, "pf_bgnet_forward: labels / depth / mask must be 16-byte aligned");
+          // the maps depend on the caller's pointers: re-encode and upload (stream-ordered) only when they change
+          if (!net->first_maps_dev) PF_CHECK_CUDA(cudaMalloc(&net->first_maps_dev, sizeof(FirstMaps)));
+          if (net->fm_labels != labels_dev || net->fm_depth != depth_dev || net->fm_mask != mask_dev || net->fm_b != b ||
+              net->fm_H != H || net->fm_W != W) {
+            FirstMaps fm;
+            int rc = first_conv_maps(&fm, labels_dev, depth_dev, mask_dev, b * net->num_inputs, H, W, net->use_depth != 0);
+            if (rc) return rc;
+            PF_CHECK_CUDA(cudaMemcpyAsync(net->first_maps_dev, &fm, sizeof(FirstMaps), cudaMemcpyHostToDevice, st));
+            net->fm_labels = labels_dev; net->fm_depth = depth_dev; net->fm_mask = mask_dev;
+            net->fm_b = b; net->fm_H = H; net->fm_W = W;
+          }
+          p.maps = reinterpret_cast<const FirstMaps*>(net->first_maps_dev);
+        }
+        p.tab = net->first_tab_dev;
         p.out = a.ptr(c.out.buf, 0); p.out_lo = a.ptr_lo(c.out.buf, 0); p.split = split;
         p.b = b; p.t = net->num_inputs; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2;
         p.ncls = net->num_classes; p.use_depth = net->use_depth; p.mean = net->depth_mean; p.std = net->depth_std;
-        const size_t smem = net->first_tab_floats * 4 + (size_t)p.t * F_IH * F_IW * 5 + 16;
+        const size_t smem = net->first_tab_floats * 4 + (size_t)p.t * (F_DFRAME * 4 + 2 * F_LFRAME) + 256;
+        {
+          const size_t lut_n = (size_t)9 * p.t * (p.ncls + 1) * 16, wd_n = (size_t)9 * p.t * 16;
+          PF_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_first_wd, net->first_tab_dev + lut_n, (wd_n + 16) * sizeof(float), 0,
+                                                cudaMemcpyDeviceToDevice, st));
+        }
         static bool attr_set = false;
         if (!attr_set) {
           PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
