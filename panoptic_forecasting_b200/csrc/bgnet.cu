@@ -85,13 +85,18 @@ struct pf_bgnet {
     const void* ws = nullptr; int b = 0, H = 0, W = 0;
     CUtensorMap* maps_dev = nullptr;
     std::vector<TcLayer> layers;             // indexed by conv (per-tap kernel: 1x1 convs, fallbacks)
-    std::vector<HaloLayer> halos;            // indexed by conv (halo kernel: 3x3 stride-1 convs)
+    std::vector<HaloLayer> halos;            // indexed by conv (halo kernel: 3x3 stride-1 and 1x1 convs)
+    std::vector<HaloLayer> halos_low;        // indexed by conv: low-resolution half of a fused conv1x1_up
+    std::vector<int> nblocks_low;
+    std::vector<size_t> smem_low;
     std::vector<int> nblocks;
     std::vector<size_t> smem;
     std::vector<char> use_tc;                // 0 SIMT, 1 per-tap tcgen05, 2 halo tcgen05
   } plan;
   bool force_simt = false;                   // PF_TC_FORCE_SIMT=1: run every conv on the SIMT kernels (A/B checks)
   bool no_halo = false;                      // PF_TC_NO_HALO=1: 3x3 convs on the per-tap tcgen05 kernel
+  bool fuse_up = false;                      // conv1x1_up fused with TransitionUp (tensor-core path, see ConvDesc::up_nseg)
+  float* zero_bias_dev = nullptr;
   // optional per-step CUDA-event profiling (bench.py roofline): ring of [iters][steps+1] events
   std::vector<cudaEvent_t> prof_ev;
   int prof_cap = 0, prof_iter = 0;
@@ -221,24 +226,32 @@ static void build_topology(pf_bgnet* net) {
   for (int j = 0; j < 4; ++j) {
     const int i = 3 - j;
     const int shift = 2 + i;
-    // the upsampled tensor keeps the (padded) slot layout of its source slices, so conv1x1_up
-    // reads it as the same list of slices followed by the skip's slices (hardnet.py:256 cat order).
-    int ctot = 0;
-    for (auto& s : cur_segs) ctot += s.cpad();
-    int ubuf = net->new_buf(shift, ctot);
     std::vector<SegRef> cat_in;
-    {
+    int ybuf = -1;
+    if (net->fuse_up) {
+      // conv1x1_up reads the LOW-resolution slices directly (see ConvDesc::up_nseg); no upsampled tensor
+      for (auto& s : cur_segs) cat_in.push_back(s);
+      ybuf = net->new_buf(shift + 1, (((cur_ch + skip_ch[i]) / 2) + 15) / 16 * 16);
+      net->bufs[ybuf].always_f32 = true;
+    } else {
+      // the upsampled tensor keeps the (padded) slot layout of its source slices, so conv1x1_up
+      // reads it as the same list of slices followed by the skip's slices (hardnet.py:256 cat order).
+      int ctot = 0;
+      for (auto& s : cur_segs) ctot += s.cpad();
+      int ubuf = net->new_buf(shift, ctot);
       int off = 0;
       for (auto& s : cur_segs) { SegRef u{ubuf, off, s.c}; cat_in.push_back(u); off += s.cpad(); }
+      SegRef uout{ubuf, 0, ctot};
+      Step st; st.type = STEP_UPSAMPLE; st.in = cur_segs; st.out = uout; net->steps.push_back(st);
     }
-    SegRef uout{ubuf, 0, ctot};
-    { Step st; st.type = STEP_UPSAMPLE; st.in = cur_segs; st.out = uout; net->steps.push_back(st); }
+    const int n_up = (int)cur_segs.size();
     for (auto& s : skips[i]) cat_in.push_back(s);
     const int ccat = cur_ch + skip_ch[i];
     const int chalf = ccat / 2;
     char nm[64];
     snprintf(nm, sizeof(nm), "model.conv1x1_up.%d", j);
     int c1 = net->add_conv(nm, ccat, chalf, 1, 1, cat_in, SegRef());
+    if (net->fuse_up) { net->convs[c1].up_nseg = n_up; net->convs[c1].ybuf = ybuf; }
     { Step st; st.type = STEP_CONV; st.conv = c1; net->steps.push_back(st); }
     snprintf(nm, sizeof(nm), "model.denseBlocksUp.%d", j);
     SegRef in_slot; std::vector<SegRef> outs; int oc;
@@ -249,6 +262,7 @@ static void build_topology(pf_bgnet* net) {
   }
   // finalConv (hardnet.py:325-327,371): 1x1 + bias, no BN / ReLU
   net->quarter_buf = net->new_buf(2, 16);
+  net->bufs[net->quarter_buf].always_f32 = true;
   SegRef qout{net->quarter_buf, 0, net->num_classes};
   net->final_conv = net->add_conv("model.finalConv", cur_ch, net->num_classes, 1, 1, cur_segs, qout, false);
   { Step st; st.type = STEP_HEAD; st.conv = net->final_conv; net->steps.push_back(st); }
@@ -785,15 +799,16 @@ struct Arena {
 
   void* ptr(int buf, int coff) const { return base + off[buf] + (size_t)coff * (split_buf(buf) ? 2 : 4); }
   void* ptr_lo(int buf, int coff) const { return split_buf(buf) ? base + off_lo[buf] + (size_t)coff * 2 : nullptr; }
-  bool split_buf(int buf) const { return split && buf != quarter; }
-  int quarter = -1;
+  bool split_buf(int buf) const { return split && !f32[buf]; }
+  std::vector<char> f32;          // buffers that stay fp32 under split storage
 };
 
 static void make_arena(const pf_bgnet* net, void* ws, int b, int H, int W, Arena* a) {
   a->base = ws ? reinterpret_cast<char*>(align_up((size_t)ws, 256)) : nullptr;
   a->b = b; a->H = H; a->W = W;
   a->split = net->precision == 1;
-  a->quarter = net->quarter_buf;
+  a->f32.resize(net->bufs.size());
+  for (size_t i = 0; i < net->bufs.size(); ++i) a->f32[i] = net->bufs[i].always_f32 ? 1 : 0;
   const size_t nb = net->bufs.size();
   a->off.resize(nb); a->off_lo.resize(nb); a->img_elems.resize(nb);
   size_t off = 0;
@@ -942,7 +957,7 @@ static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUte
   L->Hout = io.Hout; L->Wout = io.Wout;
   L->tiles_x = cdiv(io.Wout, 16); L->tiles_y = cdiv(io.Hout, 8);
   L->ntile = ntile; L->stages = stages; L->tmem_cols = cols;
-  L->cout_store = io.out_f32 ? 16 : (c.s2d_out ? 32 : padc(c.cout));
+  L->cout_store = (io.out_f32 && i == net->final_conv) ? 16 : (c.s2d_out ? 32 : padc(c.cout));
   L->relu = c.relu ? 1 : 0;
   L->out_hi = reinterpret_cast<__nv_bfloat16*>(io.out_hi);
   L->out_lo = reinterpret_cast<__nv_bfloat16*>(io.out_lo);
@@ -955,8 +970,9 @@ static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUte
 // Halo-kernel plan of a 3x3 / stride-1 conv.  Returns 1 when the layer does not fit (caller falls
 // back to the per-tap kernel), 0 on success, <0 / cudaError on failure.
 static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUtensorMap>* maps, HaloLayer* L,
-                            int* nblocks, size_t* smem) {
+                            int* nblocks, size_t* smem, int seg0 = 0, int seg1 = -1) {
   const ConvDesc& c = net->convs[i];
+  if (seg1 < 0) seg1 = (int)c.in.size();
   if (c.exec_stride() != 1) return 1;
   memset(L, 0, sizeof(*L));
   const int taps = c.ksize * c.ksize;
@@ -966,26 +982,29 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   int ntile, nb, stages, cols;
   size_t dummy;
   tc_pick_tiling(c.coutpad, cdiv(io.Wout, 8) * cdiv(io.Hout, 16) * io.b, &ntile, &nb, &stages, &cols, &dummy);
-  L->nseg = (int)c.in.size();
+  L->nseg = seg1 - seg0;
   L->ntile = ntile;
   int kb = 0;
   bool used[3] = {false, false, false};
-  for (int s = 0; s < L->nseg; ++s) {
+  for (int s = 0; s < (int)c.in.size(); ++s) {       // K offsets run over ALL slices; only [seg0, seg1) are read
     const int cp = c.in[s].cpad();
-    L->seg_cpad[s] = cp;
-    L->seg_w[s] = halo_chunk_width(cp);
-    used[L->seg_w[s] >> 5] = true;
-    L->seg_koff[s] = kb;
+    if (s >= seg0 && s < seg1) {
+      L->seg_cpad[s - seg0] = cp;
+      L->seg_w[s - seg0] = halo_chunk_width(cp);
+      used[L->seg_w[s - seg0] >> 5] = true;
+      L->seg_koff[s - seg0] = kb;
+    }
     kb += taps * cp;
   }
   if (!halo_plan_smem(L, smem)) return 1;
-  for (int s = 0; s < L->nseg; ++s) {
-    L->seg_map[s] = (int)maps->size();
+  for (int s = seg0; s < seg1; ++s) {
+    const int k = s - seg0;
+    L->seg_map[k] = (int)maps->size();
     CUtensorMap m;
-    int rc = halo_encode_act_map(&m, io.in_hi[s], L->seg_cpad[s], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[s], L->hx, L->hy);
+    int rc = halo_encode_act_map(&m, io.in_hi[s], L->seg_cpad[k], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[k], L->hx, L->hy);
     if (rc) return rc;
     maps->push_back(m);
-    rc = halo_encode_act_map(&m, io.in_lo[s], L->seg_cpad[s], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[s], L->hx, L->hy);
+    rc = halo_encode_act_map(&m, io.in_lo[s], L->seg_cpad[k], io.in_cs[s], io.Win, io.Hin, io.b, io.in_img[s], L->seg_w[k], L->hx, L->hy);
     if (rc) return rc;
     maps->push_back(m);
   }
@@ -1010,7 +1029,7 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   int tcols = 32;
   while (tcols < 4 * ntile) tcols <<= 1;
   L->tmem_cols = tcols;
-  L->cout_store = io.out_f32 ? 16 : (c.s2d_out ? 32 : padc(c.cout));
+  L->cout_store = (io.out_f32 && i == net->final_conv) ? 16 : (c.s2d_out ? 32 : padc(c.cout));
   L->relu = c.relu ? 1 : 0;
   L->out_hi = reinterpret_cast<__nv_bfloat16*>(io.out_hi);
   L->out_lo = reinterpret_cast<__nv_bfloat16*>(io.out_lo);
@@ -1027,7 +1046,14 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
   const size_t nc = net->convs.size();
   P.layers.assign(nc, TcLayer());
   P.halos.assign(nc, HaloLayer());
+  P.halos_low.assign(nc, HaloLayer());
+  P.nblocks_low.assign(nc, 0);
+  P.smem_low.assign(nc, 0);
   P.nblocks.assign(nc, 0);
+  if (!net->zero_bias_dev) {
+    PF_CHECK_CUDA(cudaMalloc(&net->zero_bias_dev, 512 * sizeof(float)));
+    PF_CHECK_CUDA(cudaMemset(net->zero_bias_dev, 0, 512 * sizeof(float)));
+  }
   P.smem.assign(nc, 0);
   P.use_tc.assign(nc, 0);
   for (size_t i = 0; i < nc; ++i) {
@@ -1048,6 +1074,30 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
     io.out_lo = head ? nullptr : a.ptr_lo(c.out.buf, c.out.coff);
     io.out_f32 = head ? reinterpret_cast<float*>(a.ptr(c.out.buf, c.out.coff)) : nullptr;
     io.out_cs = ob.cstride; io.out_img = a.img_elems[c.out.buf];
+    if (c.up_nseg > 0) {
+      // fused conv1x1_up: (1) low-resolution 1x1 over the first up_nseg slices -> fp32 ybuf (no bias / ReLU)
+      const BufDesc& yb = net->bufs[c.ybuf];
+      TcIo lo = io;
+      lo.Hin = lo.Hout = a.H >> yb.shift; lo.Win = lo.Wout = a.W >> yb.shift;
+      lo.out_hi = lo.out_lo = nullptr;
+      lo.out_f32 = reinterpret_cast<float*>(a.ptr(c.ybuf, 0));
+      lo.out_cs = yb.cstride; lo.out_img = a.img_elems[c.ybuf];
+      int rc = build_halo_layer(net, (int)i, lo, &maps, &P.halos_low[i], &P.nblocks_low[i], &P.smem_low[i], 0, c.up_nseg);
+      PF_REQUIRE(rc == 0, rc == 1 ? PF_EINVAL : rc, "fused conv1x1_up: low-resolution plan failed for %s", c.name.c_str());
+      P.halos_low[i].relu = 0;
+      P.halos_low[i].bias = net->zero_bias_dev;
+      // (2) high-resolution 1x1 over the skip slices + bilinear(ybuf) + bias + ReLU
+      TcIo hi = io;                                   // the skip slices live at the output resolution
+      hi.Hin = io.Hout; hi.Win = io.Wout;
+      rc = build_halo_layer(net, (int)i, hi, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i], c.up_nseg, (int)c.in.size());
+      PF_REQUIRE(rc == 0, rc == 1 ? PF_EINVAL : rc, "fused conv1x1_up: high-resolution plan failed for %s", c.name.c_str());
+      HaloLayer& hl = P.halos[i];
+      hl.add_src = lo.out_f32; hl.add_H = lo.Hout; hl.add_W = lo.Wout; hl.add_cs = lo.out_cs; hl.add_img = lo.out_img;
+      hl.add_sh = io.Hout > 1 ? (float)(lo.Hout - 1) / (float)(io.Hout - 1) : 0.f;
+      hl.add_sw = io.Wout > 1 ? (float)(lo.Wout - 1) / (float)(io.Wout - 1) : 0.f;
+      P.use_tc[i] = 3;
+      continue;
+    }
     const bool need_halo = c.s2d_in || c.s2d_out;
     int rc = (net->no_halo && !need_halo) ? 1 : build_halo_layer(net, (int)i, io, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i]);
     if (rc == 0) { P.use_tc[i] = 2; continue; }
@@ -1082,6 +1132,10 @@ extern "C" int pf_bgnet_create(pf_bgnet_t** out, int num_classes, int num_inputs
   net->force_simt = fs && fs[0] == '1';
   const char* nh = getenv("PF_TC_NO_HALO");
   net->no_halo = nh && nh[0] == '1';
+  // opt-in (PF_TC_FUSE_UP=1): measured 0.9 % slower than the separate upsample kernel at batch 8 -- the gather
+  // of the low-resolution partial in the epilogue costs more than the upsample kernel + wider 1x1 it replaces
+  const char* nf = getenv("PF_TC_FUSE_UP");
+  net->fuse_up = precision == 1 && !net->force_simt && !net->no_halo && (nf && nf[0] == '1');
   build_topology(net);
   *out = net;
   return 0;
@@ -1094,6 +1148,7 @@ extern "C" void pf_bgnet_destroy(pf_bgnet_t* net) {
     if (c.bias_dev) cudaFree(c.bias_dev);
   }
   for (auto p : net->wtc_dev) if (p) cudaFree(p);
+  if (net->zero_bias_dev) cudaFree(net->zero_bias_dev);
   if (net->plan.maps_dev) cudaFree(net->plan.maps_dev);
   if (net->first_tab_dev) cudaFree(net->first_tab_dev);
   if (net->first_maps_dev) cudaFree(net->first_maps_dev);
@@ -1226,7 +1281,10 @@ extern "C" size_t pf_bgnet_workspace_bytes(const pf_bgnet_t* net, int b, int H, 
 extern "C" int pf_bgnet_launches_per_forward(const pf_bgnet_t* net) {
   if (!net) return PF_EINVAL;
   int n = 0;
-  for (auto& s : net->steps) n += (s.type == STEP_HEAD) ? 2 : 1;
+  for (auto& s : net->steps) {
+    n += (s.type == STEP_HEAD) ? 2 : 1;
+    if (s.type == STEP_CONV && net->convs[s.conv].up_nseg > 0) n += 1;
+  }
   return n;
 }
 
@@ -1234,6 +1292,11 @@ extern "C" int pf_bgnet_launches_per_forward(const pf_bgnet_t* net) {
 static int run_conv(pf_bgnet* net, const Arena& a, int ci, cudaStream_t st) {
   const ConvDesc& c = net->convs[ci];
   const bool head = ci == net->final_conv;
+  if (net->precision == 1 && !net->force_simt && net->plan.use_tc[ci] == 3) {
+    int rc = launch_conv_halo(net->plan.halos_low[ci], net->plan.maps_dev, net->plan.nblocks_low[ci], net->plan.smem_low[ci], st);
+    if (rc) return rc;
+    return launch_conv_halo(net->plan.halos[ci], net->plan.maps_dev, net->plan.nblocks[ci], net->plan.smem[ci], st);
+  }
   if (net->precision == 1 && !net->force_simt && net->plan.use_tc[ci] == 2)
     return launch_conv_halo(net->plan.halos[ci], net->plan.maps_dev, net->plan.nblocks[ci], net->plan.smem[ci], st);
   if (net->precision == 1 && !net->force_simt && net->plan.use_tc[ci] == 1)

@@ -21,6 +21,7 @@ struct BufDesc {
   int shift = 0;                 // spatial size = (H >> shift, W >> shift)
   int cstride = 0;               // channels per pixel (sum of padded slots)
   size_t offset_floats = 0;      // per-image offset inside the arena, filled at plan time
+  bool always_f32 = false;       // fp32 even with split-bf16 storage (quarter-res logits, low-res conv1x1_up partials)
 };
 
 struct ConvDesc {
@@ -39,6 +40,12 @@ struct ConvDesc {
   // half its resolution) so that base.2, the only 3x3 STRIDE-2 ConvLayer besides the first, runs as a
   // stride-1 conv with 4 active taps over that tensor on the tcgen05 halo kernel.
   bool s2d_out = false, s2d_in = false;
+  // tensor-core path only: conv1x1_up fused with TransitionUp.  A 1x1 conv commutes with the (per-channel,
+  // linear) bilinear upsample, so the first `up_nseg` input slices are convolved at LOW resolution into the fp32
+  // buffer `ybuf` (no bias / ReLU) and the high-resolution pass over the skip slices adds its bilinear
+  // interpolation in the epilogue: relu(W_skip * skip + up(W_up * x) + b).  No upsampled tensor is materialised.
+  int up_nseg = 0;
+  int ybuf = -1;
   int exec_stride() const { return s2d_in ? 1 : stride; }
   std::vector<float> w_host;     // folded, packed like w_dev (kept for re-packing by the tensor-core path)
   std::vector<float> bias_host;

@@ -281,6 +281,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
                              ? (size_t)img * L.out_img_stride + ((size_t)(oy >> 1) * (L.Wout >> 1) + (ox >> 1)) * L.out_cs +
                                    (size_t)((oy & 1) * 2 + (ox & 1)) * L.s2d_block
                              : (size_t)img * L.out_img_stride + ((size_t)oy * L.Wout + ox) * L.out_cs;
+      // bilinear source of the optional additive term (conv1x1_up fused with TransitionUp)
+      const float *a00 = nullptr, *a01 = nullptr, *a10 = nullptr, *a11 = nullptr;
+      float aly = 0.f, alx = 0.f;
+      if (L.add_src && inside) {
+        const float fy = L.add_sh * (float)oy, fx = L.add_sw * (float)ox;
+        const int ay0 = (int)fy, ax0 = (int)fx;
+        const int ay1 = ay0 + (ay0 < L.add_H - 1 ? 1 : 0), ax1 = ax0 + (ax0 < L.add_W - 1 ? 1 : 0);
+        aly = fy - (float)ay0; alx = fx - (float)ax0;
+        const float* ab = L.add_src + (size_t)img * L.add_img;
+        a00 = ab + ((size_t)ay0 * L.add_W + ax0) * L.add_cs; a01 = ab + ((size_t)ay0 * L.add_W + ax1) * L.add_cs;
+        a10 = ab + ((size_t)ay1 * L.add_W + ax0) * L.add_cs; a11 = ab + ((size_t)ay1 * L.add_W + ax1) * L.add_cs;
+      }
       for (int c = 0; c < ntile; c += 16) {
         const int n = n0 + c;
         if (n >= L.cout_store) break;
@@ -288,9 +300,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
         tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * ntile + c), v);
         tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * ntile + ntile + c), v2);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          v[i] = (v[i] + v2[i]) + __ldg(L.bias + n + i);
-          if (L.relu) v[i] = fmaxf(v[i], 0.f);
+        for (int i = 0; i < 16; ++i) v[i] = (v[i] + v2[i]) + __ldg(L.bias + n + i);
+        if (a00) {
+          const float ahy = 1.f - aly, ahx = 1.f - alx;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(a00 + n) + i), q4 = __ldg(reinterpret_cast<const float4*>(a01 + n) + i);
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(a10 + n) + i), s4 = __ldg(reinterpret_cast<const float4*>(a11 + n) + i);
+            v[4 * i + 0] += ahy * (ahx * p.x + alx * q4.x) + aly * (ahx * r4.x + alx * s4.x);
+            v[4 * i + 1] += ahy * (ahx * p.y + alx * q4.y) + aly * (ahx * r4.y + alx * s4.y);
+            v[4 * i + 2] += ahy * (ahx * p.z + alx * q4.z) + aly * (ahx * r4.z + alx * s4.z);
+            v[4 * i + 3] += ahy * (ahx * p.w + alx * q4.w) + aly * (ahx * r4.w + alx * s4.w);
+          }
+        }
+        if (L.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (!inside) continue;
         if (L.out_f32) {

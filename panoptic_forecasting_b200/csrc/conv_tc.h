@@ -51,6 +51,11 @@ struct HaloLayer {
   int out_cs;
   size_t out_img_stride;
   const float* bias;
+  // optional epilogue term: + bilinear(align_corners) interpolation of an fp32 NHWC tensor at the output pixel
+  const float* add_src;
+  int add_H, add_W, add_cs;
+  size_t add_img;
+  float add_sh, add_sw;
   long long* dbg_ts;        // optional: CTA 0 writes phase timestamps (clock64) here
 };
 

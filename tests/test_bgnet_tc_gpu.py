@@ -76,3 +76,15 @@ def test_every_conv_layer_tcgen05_per_tap_kernel(pf_lib, bg_shapes, monkeypatch)
     monkeypatch.delenv("PF_TC_FORCE_SIMT", raising=False)
     monkeypatch.setenv("PF_TC_NO_HALO", "1")
     layer_sweep(pf_lib, bg_shapes, 1e-4)
+
+
+def test_fused_conv1x1_up_path(pf_lib, bg_shapes, monkeypatch):
+    """PF_TC_FUSE_UP=1: conv1x1_up commuted with the bilinear TransitionUp (low-res 1x1 + gather epilogue)."""
+    monkeypatch.setenv("PF_TC_FUSE_UP", "1")
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=7)
+    pc = synthetic.make_pc_inputs(1, 3, 128, 256, "R", seed=7)
+    inp = {"seg": pc["seg"].long(), "depth": pc["depth"].clamp(0.1, 200), "depth_mask": pc["depth_mask"]}
+    ref = bg_oracle.predict(sd, inp, None)
+    out = gpu_model(sd, None, precision="tc").predict({k: v.cuda() for k, v in inp.items()}, {})
+    scale = ref["logits"].abs().max().item()
+    assert (out["logits"].cpu() - ref["logits"]).abs().max().item() <= 3e-4 * scale
