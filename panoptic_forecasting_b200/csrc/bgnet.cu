@@ -95,6 +95,7 @@ struct pf_bgnet {
   } plan;
   bool force_simt = false;                   // PF_TC_FORCE_SIMT=1: run every conv on the SIMT kernels (A/B checks)
   bool no_halo = false;                      // PF_TC_NO_HALO=1: 3x3 convs on the per-tap tcgen05 kernel
+  bool compact_slots = true;                 // HarDBlock slots are separate compact tensors (PF_INTERLEAVED_SLOTS=1: one wide buffer per block)
   bool fuse_up = false;                      // conv1x1_up fused with TransitionUp (tensor-core path, see ConvDesc::up_nseg)
   float* zero_bias_dev = nullptr;
   // optional per-step CUDA-event profiling (bench.py roofline): ring of [iters][steps+1] events
@@ -129,17 +130,26 @@ static void build_block(pf_bgnet* net, const std::string& prefix, int in_ch, int
   std::vector<int> ch(n_layers + 1), off(n_layers + 1);
   ch[0] = in_ch;
   for (int l = 1; l <= n_layers; ++l) get_link(l, in_ch, gr, &ch[l], nullptr);
-  int total = 0;
-  for (int l = 0; l <= n_layers; ++l) { off[l] = total; total += padc(ch[l]); }
-  const int buf = net->new_buf(shift, total);
-  in_slot->buf = buf; in_slot->coff = 0; in_slot->c = in_ch;
+  // Every slot (block input, each layer's output) is its own compact NHWC tensor: a consumer's TMA boxes and a
+  // producer's stores then touch whole DRAM pages instead of 32..96-byte pieces of a wide interleaved row
+  // (the interleaved block buffer made the 1/4-resolution layers ~1.8x slower on B200).
+  std::vector<int> bufs(n_layers + 1);
+  if (net->compact_slots) {
+    for (int l = 0; l <= n_layers; ++l) { off[l] = 0; bufs[l] = net->new_buf(shift, padc(ch[l])); }
+  } else {
+    int total = 0;
+    for (int l = 0; l <= n_layers; ++l) { off[l] = total; total += padc(ch[l]); }
+    const int buf = net->new_buf(shift, total);
+    for (int l = 0; l <= n_layers; ++l) bufs[l] = buf;
+  }
+  in_slot->buf = bufs[0]; in_slot->coff = 0; in_slot->c = in_ch;
   for (int l = 1; l <= n_layers; ++l) {
     int oc; std::vector<int> link;
     get_link(l, in_ch, gr, &oc, &link);
     std::vector<SegRef> in;
     int cin = 0;
-    for (int k : link) { SegRef s; s.buf = buf; s.coff = off[k]; s.c = ch[k]; in.push_back(s); cin += ch[k]; }
-    SegRef out; out.buf = buf; out.coff = off[l]; out.c = oc;
+    for (int k : link) { SegRef s; s.buf = bufs[k]; s.coff = off[k]; s.c = ch[k]; in.push_back(s); cin += ch[k]; }
+    SegRef out; out.buf = bufs[l]; out.coff = off[l]; out.c = oc;
     char nm[96];
     snprintf(nm, sizeof(nm), "%s.layers.%d", prefix.c_str(), l - 1);
     int ci = net->add_conv(nm, cin, oc, 3, 1, in, out);
@@ -151,7 +161,7 @@ static void build_block(pf_bgnet* net, const std::string& prefix, int in_ch, int
   const int t = n_layers + 1;
   for (int i = 0; i < t; ++i) {
     if (i == t - 1 || i % 2 == 1) {
-      SegRef s; s.buf = buf; s.coff = off[i]; s.c = ch[i];
+      SegRef s; s.buf = bufs[i]; s.coff = off[i]; s.c = ch[i];
       out_segs->push_back(s);
       *out_ch_total += ch[i];
     }
@@ -1136,6 +1146,8 @@ extern "C" int pf_bgnet_create(pf_bgnet_t** out, int num_classes, int num_inputs
   // of the low-resolution partial in the epilogue costs more than the upsample kernel + wider 1x1 it replaces
   const char* nf = getenv("PF_TC_FUSE_UP");
   net->fuse_up = precision == 1 && !net->force_simt && !net->no_halo && (nf && nf[0] == '1');
+  const char* il = getenv("PF_INTERLEAVED_SLOTS");
+  net->compact_slots = !(il && il[0] == '1');
   build_topology(net);
   *out = net;
   return 0;
@@ -1576,21 +1588,26 @@ extern "C" int pf_bgnet_debug_conv(pf_bgnet_t* net, int i, const float* x_nchw_d
       PF_CHECK_CUDA(cudaStreamSynchronize(st));
       long long* ts_dev = nullptr;
       if (kind == 2 && getenv("PF_HALO_TS")) {
-        cudaMalloc(&ts_dev, 16 * sizeof(long long));
-        cudaMemset(ts_dev, 0, 16 * sizeof(long long));
+        cudaMalloc(&ts_dev, 96 * sizeof(long long));
+        cudaMemset(ts_dev, 0, 96 * sizeof(long long));
         HL.dbg_ts = ts_dev;
+        HL.dbg_mode = atoi(getenv("PF_HALO_TS")) >> 1;   // PF_HALO_TS=1 plain, 3 no-TMA, 5 no-stores, 7 both
         launch_conv_halo(HL, maps_dev, nblocks, smem, st);      // warm (weights / descriptors in L2)
       }
       rc = kind == 2 ? launch_conv_halo(HL, maps_dev, nblocks, smem, st) : launch_conv_tc(L, maps_dev, nblocks, b, smem, st);
       if (ts_dev) {
-        long long ts[16];
+        long long ts[96];
         cudaStreamSynchronize(st);
         cudaMemcpy(ts, ts_dev, sizeof(ts), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[halo ts] %s tiles=%d nblk=%d res=%d SA=%d SB=%d ntile=%d: setup %lld, w-ready %lld, first-A %lld, "
-                "tile0 mma-issued %lld, tile0 acc-ready %lld, tile0 epi-done %lld, all-mma-issued %lld, end %lld (cycles)\n",
+                "tile0 mma-issued %lld, tile0 acc-ready %lld, tile0 epi-done %lld, all-mma-issued %lld, end %lld; waits: "
+                "mma<-A %lld, mma<-tmem %lld, tma<-emptyA %lld, epi<-acc %lld (cycles)\n",
                 c.name.c_str(), HL.tiles_x * HL.tiles_y * HL.batch, nblocks, HL.resident, HL.stages_a, HL.stages_b, HL.ntile,
                 ts[1] - ts[0], ts[2] - ts[0], ts[3] - ts[0], ts[4] - ts[0], ts[5] - ts[0], ts[6] - ts[0], ts[7] - ts[0],
-                ts[8] - ts[0]);
+                ts[8] - ts[0], ts[9], ts[10], ts[11], ts[12]);
+        for (int k = 0; k < 24; ++k)
+          fprintf(stderr, "   chunk %2d: tma-issued %7lld  a-ready %7lld  mma-issued %7lld\n", k, ts[16 + k] - ts[0], ts[40 + k] - ts[0],
+                  ts[64 + k] - ts[0]);
         cudaFree(ts_dev);
       }
     }

@@ -41,57 +41,131 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 }  // namespace
 
-// All MMAs of one staged activation chunk: TAPS filter taps x (W/16) K atoms x 2 MMAs.  Fully unrolled
-// with W / TAPS as template parameters so that every descriptor offset is an immediate: the issue rate
-// of these small-N MMAs is bound by the uniform-datapath instructions between them, not by the tensor pipe.
+// All MMAs of one staged activation chunk: KS x KS filter taps x NK K-atoms x 2 MMAs.
+// Everything that shapes the instruction stream is a template parameter (chunk width W, atoms NK, taps, weight
+// residency), the dy loop stays rolled and the dx / atom loops are unrolled with immediate descriptor offsets.
+// The issuing warp is a single instruction stream feeding a tensor pipe that retires one of these small-N MMAs
+// every ~40 cycles (shared-memory operand fetch: (4 KB of A + N x 32 B of B) / 128 B per clock, measured), so
+// its code has to be branch-free and small enough to stay in the instruction cache: the earlier fully unrolled,
+// runtime-predicated version spent 38% of its issue slots in instruction-fetch stalls (ncu source view).
 struct ChunkIssue {
   uint32_t d, idesc1, idesc2, el;
   uint32_t sa, a_tile;          // A stage: hi plane at sa, lo plane at sa + a_tile
-  int nk, tap_mask;
-  // weights: resident -> walk `woff` from smem_base; streamed -> B ring
-  int resident;
-  uint32_t smem_base, pair_step;          // resident: bytes between consecutive taps' [hi;lo] tiles
+  uint32_t smem_base, ntile4;             // resident weights: tap tiles [hi rows ; lo rows] are align1k(4 * ntile * W) bytes apart
   uint32_t b_base, b_tile, bar_full_b0, bar_empty_b0;
   int SB;
 };
 
-template <int W, int TAPS, bool FIRST>   // FIRST: first chunk of a tile -> its first MMA overwrites the accumulator
-__device__ __forceinline__ void issue_chunk(const ChunkIssue& c, uint32_t& woff, int& ib) {
-  constexpr int HX = TAPS == 9 ? 10 : 8;
+template <int W, int NK, int KS, bool RES>
+__device__ __forceinline__ void issue_chunk(const ChunkIssue& c, uint32_t acc_first, uint32_t& woff, int& ib) {
+  constexpr int HX = KS == 1 ? 8 : 10;
   constexpr uint32_t RP = 2u * W;
   constexpr uint32_t LAY = W == 64 ? 2u : (W == 32 ? 4u : 6u);
   constexpr uint32_t A_HI = ((HX * RP) >> 4) | (1u << 14) | (LAY << 29);   // SBO | version | swizzle (upper descriptor word)
   constexpr uint32_t B_HI = ((8u * RP) >> 4) | (1u << 14) | (LAY << 29);
-  const uint32_t a_hi_lo = ((c.sa & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t a_lo_lo = (((c.sa + c.a_tile) & 0x3FFFFu) >> 4) | (1u << 16);
+  uint32_t a_hi_lo = ((c.sa & 0x3FFFFu) >> 4) | (1u << 16);
+  uint32_t a_lo_lo = (((c.sa + c.a_tile) & 0x3FFFFu) >> 4) | (1u << 16);
+  uint32_t accv = acc_first;
+#pragma unroll 1
+  for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
-  for (int tap = 0; tap < TAPS; ++tap) {
-    if (!((c.tap_mask >> tap) & 1)) continue;
-    constexpr int dummy = 0; (void)dummy;
-    const uint32_t shift = (uint32_t)(((tap / 3) * HX + (tap % 3)) * (int)(RP >> 4));   // immediate after unrolling
-    uint32_t sb;
-    int sbi = 0;
-    if (c.resident) {
-      sb = c.smem_base + woff;
-      woff += c.pair_step;
-    } else {
-      sbi = ib % c.SB;
-      mbar_wait(c.bar_full_b0 + 8u * sbi, (ib / c.SB) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      sb = c.b_base + sbi * c.b_tile;
-      ++ib;
-    }
-    const uint32_t b_lo = ((sb & 0x3FFFFu) >> 4) | (1u << 16);
-#pragma unroll
-    for (int ka = 0; ka < W / 16; ++ka) {
-      if (ka < c.nk) {
-        // tap 0 is active in every tap mask, so (tap 0, atom 0) of the first chunk is the tile's first MMA
-        umma_bf16_w(c.d, a_hi_lo + shift + 2 * ka, A_HI, b_lo + 2 * ka, B_HI, c.idesc2, (FIRST && tap == 0 && ka == 0) ? 0u : 1u, c.el);
-        umma_bf16_w(c.d, a_lo_lo + shift + 2 * ka, A_HI, b_lo + 2 * ka, B_HI, c.idesc1, 1u, c.el);
+    for (int dx = 0; dx < KS; ++dx) {
+      uint32_t sb;
+      int sbi = 0;
+      if (RES) {
+        sb = c.smem_base + woff;
+        woff += align1k(c.ntile4 * (uint32_t)W);
+      } else {
+        sbi = ib % c.SB;
+        mbar_wait(c.bar_full_b0 + 8u * sbi, (ib / c.SB) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        sb = c.b_base + sbi * c.b_tile;
+        ++ib;
       }
+      const uint32_t b_lo = ((sb & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+      for (int ka = 0; ka < NK; ++ka) {
+        const uint32_t shift = (uint32_t)(dx * (int)(RP >> 4) + 2 * ka);   // immediate
+        umma_bf16_w(c.d, a_hi_lo + shift, A_HI, b_lo + 2 * ka, B_HI, c.idesc2, (dx == 0 && ka == 0) ? accv : 1u, c.el);
+        umma_bf16_w(c.d, a_lo_lo + shift, A_HI, b_lo + 2 * ka, B_HI, c.idesc1, 1u, c.el);
+      }
+      if (!RES) umma_commit_p(c.bar_empty_b0 + 8u * sbi, c.el);
     }
-    if (!c.resident) umma_commit_p(c.bar_empty_b0 + 8u * sbi, c.el);
+    a_hi_lo += (uint32_t)(HX * (int)(RP >> 4));
+    a_lo_lo += (uint32_t)(HX * (int)(RP >> 4));
+    accv = 1u;
   }
+}
+
+// chunk table entry: chunk width | atoms << 8 | slice << 12 | first channel << 16
+__host__ __device__ __forceinline__ uint32_t chunk_code(int w, int nk, int seg, int c0) {
+  return (uint32_t)w | ((uint32_t)nk << 8) | ((uint32_t)seg << 12) | ((uint32_t)c0 << 16);
+}
+
+template <int KS, bool RES>
+__device__ __forceinline__ void issue_dispatch(uint32_t code, const ChunkIssue& ci, uint32_t accf, uint32_t& woff, int& ib) {
+  switch (code & 0xFFFu) {
+    case 64u | (4u << 8): issue_chunk<64, 4, KS, RES>(ci, accf, woff, ib); break;
+    case 64u | (3u << 8): issue_chunk<64, 3, KS, RES>(ci, accf, woff, ib); break;
+    case 64u | (2u << 8): issue_chunk<64, 2, KS, RES>(ci, accf, woff, ib); break;
+    case 64u | (1u << 8): issue_chunk<64, 1, KS, RES>(ci, accf, woff, ib); break;
+    case 32u | (2u << 8): issue_chunk<32, 2, KS, RES>(ci, accf, woff, ib); break;
+    case 32u | (1u << 8): issue_chunk<32, 1, KS, RES>(ci, accf, woff, ib); break;
+    default: issue_chunk<16, 1, KS, RES>(ci, accf, woff, ib); break;
+  }
+}
+
+struct MmaCtx {
+  uint32_t el, tmem_d, smem_base, a_base, a_tile, b_base, b_tile, bar0, idesc1, idesc2;
+  int total_tiles;
+  bool dbg;
+};
+
+// The MMA warp's whole life: per tile, per chunk: wait for the staged activations, issue, release the stage.
+template <int KS, bool RES>
+__device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& m) {
+  const uint32_t el = m.el;
+  const int SA = L.stages_a, nchunk = L.nchunk, ntile = L.ntile;
+  const uint32_t full_a0 = m.bar0, empty_a0 = m.bar0 + 8u * kMaxA;
+  const uint32_t tmem_full0 = m.bar0 + 8u * (2 * kMaxA + 2 * kMaxB + 1), tmem_empty0 = tmem_full0 + 16u;
+  ChunkIssue ci;
+  ci.idesc1 = m.idesc1; ci.idesc2 = m.idesc2; ci.el = el; ci.a_tile = m.a_tile;
+  ci.smem_base = m.smem_base; ci.ntile4 = (uint32_t)ntile * 4u;
+  ci.b_base = m.b_base; ci.b_tile = m.b_tile;
+  ci.bar_full_b0 = m.bar0 + 8u * (2 * kMaxA); ci.bar_empty_b0 = m.bar0 + 8u * (2 * kMaxA + kMaxB); ci.SB = L.stages_b;
+  int ia = 0, ib = 0, st = 0, acc = 0;
+  uint32_t ph_a = 0, ph_t = 1;
+  long long wait_full = 0, wait_tmem = 0, w0 = 0;
+  uint32_t code = L.chunk[0];
+  for (int t = blockIdx.x; t < m.total_tiles; t += gridDim.x) {
+    if (m.dbg) w0 = clock64();
+    mbar_wait(tmem_empty0 + 8u * acc, ph_t);
+    if (m.dbg) wait_tmem += clock64() - w0;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    ci.d = m.tmem_d + (uint32_t)(acc * 2 * ntile);
+    uint32_t woff = 0, accf = 0;
+    for (int j = 0; j < nchunk; ++j, ++ia) {
+      const uint32_t next = L.chunk[j + 1 == nchunk ? 0 : j + 1];     // fetched while this chunk's MMAs issue
+      if (m.dbg) w0 = clock64();
+      mbar_wait(full_a0 + 8u * st, ph_a);
+      if (m.dbg) wait_full += clock64() - w0;
+      if (m.dbg && el && ia == 0) L.dbg_ts[3] = clock64();
+      if (m.dbg && el && ia < 24) L.dbg_ts[40 + ia] = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      ci.sa = m.a_base + st * 2 * m.a_tile;
+      issue_dispatch<KS, RES>(code, ci, accf, woff, ib);
+      accf = 1u;
+      if (m.dbg && el && ia < 24) L.dbg_ts[64 + ia] = clock64();
+      umma_commit_p(empty_a0 + 8u * st, el);
+      if (++st == SA) { st = 0; ph_a ^= 1u; }
+      code = next;
+    }
+    umma_commit_p(tmem_full0 + 8u * acc, el);
+    if (m.dbg && el && t == (int)blockIdx.x) L.dbg_ts[4] = clock64();
+    if (acc) ph_t ^= 1u;
+    acc ^= 1;
+  }
+  if (m.dbg && el) { L.dbg_ts[7] = clock64(); L.dbg_ts[9] = wait_full; L.dbg_ts[10] = wait_tmem; }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
@@ -169,41 +243,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
       }
       // ... and do not read the previous layer's activations before it has completed and flushed.
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      int ia = 0, ib = 0;
+      int ia = 0, ib = 0, st = 0;
+      uint32_t ph_a = 1;                      // parity to wait on for "stage free"; flips when the ring wraps
+      long long wait_acc = 0;
+      const int nchunk = L.nchunk;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int img = t / tiles_per_img;
         const int r = t - img * tiles_per_img;
         const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
         const int y0 = ty * 16, x0 = tx * 8;
-        for (int s = 0; s < L.nseg; ++s) {
-          const int cpad = L.seg_cpad[s], w = L.seg_w[s];
+        for (int j = 0; j < nchunk; ++j, ++ia) {
+          const uint32_t code = L.chunk[j];
+          const int w = (int)(code & 0xFFu), s = (int)((code >> 12) & 0xFu), c0 = (int)(code >> 16);
           const CUtensorMap* am = maps + L.seg_map[s];
-          const CUtensorMap* wm = maps + L.w_map[w >> 5];
           const uint32_t a_tx = (uint32_t)(HX * HY) * 2u * w;
-          const uint32_t b_tx = (uint32_t)ntile * 2u * w;
-          for (int c0 = 0; c0 < cpad; c0 += w, ++ia) {
-            const int st = ia % SA;
-            mbar_wait(empty_a(st), ((ia / SA) & 1) ^ 1);
-            const uint32_t sa = a_base + st * 2 * a_tile;
+          long long w0 = 0;
+          if (dbg) w0 = clock64();
+          mbar_wait(empty_a(st), ph_a);
+          if (dbg) wait_acc += clock64() - w0;
+          if (dbg && el && ia < 24) L.dbg_ts[16 + ia] = clock64();
+          const uint32_t sa = a_base + st * 2 * a_tile;
+          if ((L.dbg_mode & 1) && ia >= SA) {
+            if (el) mbar_arrive(full_a(st));
+            __syncwarp();
+          } else {
             mbar_expect_tx_p(full_a(st), 2 * a_tx, el);
             tma_load_4d_p(sa, am, full_a(st), c0, x0 - org, y0 - org, img, el);
             tma_load_4d_p(sa + a_tile, am + 1, full_a(st), c0, x0 - org, y0 - org, img, el);
-            if (!L.resident) {
-              for (int tap = 0; tap < NT; ++tap) {
-                if (!((L.tap_mask >> tap) & 1)) continue;
-                const int sb = ib % SB;
-                mbar_wait(empty_b(sb), ((ib / SB) & 1) ^ 1);
-                const uint32_t sbp = b_base + sb * b_tile;
-                mbar_expect_tx_p(full_b(sb), 2 * b_tx, el);
-                const int koff = L.seg_koff[s] + tap * cpad + c0;
-                tma_load_2d_p(sbp, wm, full_b(sb), koff, n0, el);
-                tma_load_2d_p(sbp + b_tx, wm + 1, full_b(sb), koff, n0, el);
-                ++ib;
-              }
+          }
+          if (++st == SA) { st = 0; ph_a ^= 1u; }
+          if (!L.resident) {
+            const int cpad = L.seg_cpad[s];
+            const CUtensorMap* wm = maps + L.w_map[w >> 5];
+            const uint32_t b_tx = (uint32_t)ntile * 2u * w;
+            for (int tap = 0; tap < NT; ++tap) {
+              if (!((L.tap_mask >> tap) & 1)) continue;
+              const int sb = ib % SB;
+              mbar_wait(empty_b(sb), ((ib / SB) & 1) ^ 1);
+              const uint32_t sbp = b_base + sb * b_tile;
+              mbar_expect_tx_p(full_b(sb), 2 * b_tx, el);
+              const int koff = L.seg_koff[s] + tap * cpad + c0;
+              tma_load_2d_p(sbp, wm, full_b(sb), koff, n0, el);
+              tma_load_2d_p(sbp + b_tx, wm + 1, full_b(sb), koff, n0, el);
+              ++ib;
             }
           }
         }
       }
+      if (dbg && el) L.dbg_ts[11] = wait_acc;
     }
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform loops, one elected lane issues) =====
@@ -219,47 +306,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
       const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * ntile) >> 3) << 17);
       if (L.resident) mbar_wait(wbar, 0);
       if (dbg && el) L.dbg_ts[2] = clock64();
-      int ia = 0, ib = 0, tc_ = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
-        const int acc = tc_ & 1;
-        mbar_wait(tmem_empty(acc), ((tc_ >> 1) & 1) ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_d + (uint32_t)(acc * 2 * ntile);
-        uint32_t woff = 0;
-        bool first = true;
-        for (int s = 0; s < L.nseg; ++s) {
-          const int cpad = L.seg_cpad[s], w = L.seg_w[s];
-          const uint32_t bt = (uint32_t)ntile * 2u * w;
-          for (int c0 = 0; c0 < cpad; c0 += w, ++ia) {
-            const int st = ia % SA;
-            mbar_wait(full_a(st), (ia / SA) & 1);
-            if (dbg && el && ia == 0) L.dbg_ts[3] = clock64();
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = a_base + st * 2 * a_tile;
-            ChunkIssue ci;
-            ci.d = d; ci.idesc1 = idesc1; ci.idesc2 = idesc2; ci.el = el;
-            ci.sa = sa; ci.a_tile = a_tile;
-            ci.nk = min(w, cpad - c0) >> 4; ci.tap_mask = L.tap_mask;
-            ci.resident = L.resident; ci.smem_base = smem_base; ci.pair_step = align1k(2 * bt);
-            ci.b_base = b_base; ci.b_tile = b_tile; ci.bar_full_b0 = full_b(0); ci.bar_empty_b0 = empty_b(0); ci.SB = SB;
-            const bool fc = first;
-            first = false;
-            if (NT == 9) {
-              if (w == 64) { if (fc) issue_chunk<64, 9, true>(ci, woff, ib); else issue_chunk<64, 9, false>(ci, woff, ib); }
-              else if (w == 32) { if (fc) issue_chunk<32, 9, true>(ci, woff, ib); else issue_chunk<32, 9, false>(ci, woff, ib); }
-              else { if (fc) issue_chunk<16, 9, true>(ci, woff, ib); else issue_chunk<16, 9, false>(ci, woff, ib); }
-            } else {
-              if (w == 64) { if (fc) issue_chunk<64, 1, true>(ci, woff, ib); else issue_chunk<64, 1, false>(ci, woff, ib); }
-              else if (w == 32) { if (fc) issue_chunk<32, 1, true>(ci, woff, ib); else issue_chunk<32, 1, false>(ci, woff, ib); }
-              else { if (fc) issue_chunk<16, 1, true>(ci, woff, ib); else issue_chunk<16, 1, false>(ci, woff, ib); }
-            }
-            umma_commit_p(empty_a(st), el);
-          }
-        }
-        umma_commit_p(tmem_full(acc), el);
-        if (dbg && el && tc_ == 0) L.dbg_ts[4] = clock64();
+      MmaCtx mc;
+      mc.el = el; mc.tmem_d = tmem_d; mc.smem_base = smem_base; mc.a_base = a_base; mc.a_tile = a_tile;
+      mc.b_base = b_base; mc.b_tile = b_tile; mc.bar0 = bar0; mc.total_tiles = total_tiles; mc.dbg = dbg;
+      mc.idesc1 = idesc1; mc.idesc2 = idesc2;
+      const int ks = NT == 1 ? 1 : (L.tap_mask == 0x1FF ? 3 : 2);
+      if (L.resident) {
+        if (ks == 3) mma_warp_loop<3, true>(L, mc);
+        else if (ks == 1) mma_warp_loop<1, true>(L, mc);
+        else mma_warp_loop<2, true>(L, mc);
+      } else {
+        if (ks == 3) mma_warp_loop<3, false>(L, mc);
+        else if (ks == 1) mma_warp_loop<1, false>(L, mc);
+        else mma_warp_loop<2, false>(L, mc);
       }
-      if (dbg && el) L.dbg_ts[7] = clock64();
     }
     __syncwarp();
   } else {
@@ -267,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
     const int q = warp & 3;
     const int m = q * 32 + lane;
     int tc_ = 0;
+    long long wait_epi = 0, w0 = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
       const int acc = tc_ & 1;
       const int img = t / tiles_per_img;
@@ -274,7 +335,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
       const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
       const int oy = ty * 16 + (m >> 3), ox = tx * 8 + (m & 7);
       const bool inside = (oy < L.Hout) && (ox < L.Wout);
+      if (dbg) w0 = clock64();
       mbar_wait(tmem_full(acc), (tc_ >> 1) & 1);
+      if (dbg) wait_epi += clock64() - w0;
       if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const size_t pix = L.s2d_block
@@ -317,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (!inside) continue;
+        if (!inside || (L.dbg_mode & 2)) continue;
         if (L.out_f32) {
           float4* o = reinterpret_cast<float4*>(L.out_f32 + pix + n);
 #pragma unroll
@@ -343,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
       if (lane == 0) mbar_arrive(tmem_empty(acc));
       if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[6] = clock64();
     }
+    if (dbg && threadIdx.x == 64) L.dbg_ts[12] = wait_epi;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -409,6 +473,16 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
   const size_t budget = 218 * 1024;
   int wmax = 16;
   size_t w_total = 0, w_tx = 0;
+  if (L->taps == 9 && L->tap_mask != 0x1FF && L->tap_mask != 0x1B) return false;   // the issue loops know 3x3 and the 2x2 s2d form
+  L->nchunk = 0;
+  for (int s = 0; s < L->nseg; ++s) {
+    const int w = L->seg_w[s];
+    for (int c0 = 0; c0 < L->seg_cpad[s]; c0 += w) {
+      if (L->nchunk == kHaloMaxChunks) return false;
+      const int nk = (L->seg_cpad[s] - c0 < w ? L->seg_cpad[s] - c0 : w) / 16;
+      L->chunk[L->nchunk++] = chunk_code(w, nk, s, c0);
+    }
+  }
   for (int s = 0; s < L->nseg; ++s) {
     const int w = L->seg_w[s];
     if (w > wmax) wmax = w;

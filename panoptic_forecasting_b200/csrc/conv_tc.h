@@ -28,6 +28,8 @@ struct TcLayer {
   const float* bias;
 };
 
+constexpr int kHaloMaxChunks = 32;
+
 // 3x3 / stride-1 layers on the persistent halo kernel (conv_halo.cu)
 struct HaloLayer {
   int nseg;
@@ -36,6 +38,8 @@ struct HaloLayer {
   int seg_map[kMaxSegs];    // hi-plane halo-box tensor map of the slice (lo = +1)
   int seg_koff[kMaxSegs];   // first K column of the slice in the packed weight matrix
   int w_map[3];             // weight tensor maps (hi; lo = +1) for chunk widths 16 / 32 / 64
+  int nchunk;               // staged activation chunks per tile, in K order
+  uint32_t chunk[kHaloMaxChunks];   // chunk width | K atoms << 8 | slice << 12 | first channel << 16 (halo_plan_smem fills it)
   int Hout, Wout, tiles_x, tiles_y, batch;
   int taps, hx, hy;         // 9 taps / 10 x 18 box (3x3) or 1 tap / 8 x 16 box (1x1)
   int tap_mask;             // active taps (bit dy*3+dx); 0x1FF normally, 0x1B for the space-to-depth stride-2 conv
@@ -57,6 +61,7 @@ struct HaloLayer {
   size_t add_img;
   float add_sh, add_sw;
   long long* dbg_ts;        // optional: CTA 0 writes phase timestamps (clock64) here
+  int dbg_mode;             // timing experiments only (results invalid): 1 = no activation TMA after the first ring pass, 2 = no stores
 };
 
 int halo_chunk_width(int cpad);

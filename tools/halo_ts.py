@@ -22,7 +22,8 @@ shapes = {1: (512, 1024), 3: (256, 512), 7: (256, 512), 8: (256, 512), 13: (128,
 for i in [int(a) for a in sys.argv[1:]] or sorted(shapes):
     L.pf_bgnet_conv_info(m._net, i, C.byref(info))
     H, W = shapes.get(i, (256, 512))
-    x = torch.randn(2, info.cin, H, W, device="cuda").relu()
-    y = torch.empty((2, info.cout, H // info.stride, W // info.stride), device="cuda")
-    rc = L.pf_bgnet_debug_conv(m._net, i, x.data_ptr(), 2, H, W, y.data_ptr(), None)
+    B = int(os.environ.get("PF_TS_BATCH", "2"))
+    x = torch.randn(B, info.cin, H, W, device="cuda").relu()
+    y = torch.empty((B, info.cout, H // info.stride, W // info.stride), device="cuda")
+    rc = L.pf_bgnet_debug_conv(m._net, i, x.data_ptr(), B, H, W, y.data_ptr(), None)
     assert rc == 0, L.pf_last_error()
