@@ -499,26 +499,23 @@ struct PoolParams {
   int b, Ho, Wo, c4, split;
 };
 
-__global__ void avgpool2_kernel(PoolParams p) {
-  const size_t total = (size_t)p.b * p.Ho * p.Wo * p.c4;
+// grid = (ceil(Wo * groups / 256), Ho, b): one thread per (output pixel, 8-channel group)
+__global__ void __launch_bounds__(256) avgpool2_kernel(PoolParams p) {
   const bool sp = p.split != 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % p.c4);
-    size_t r = i / p.c4;
-    const int x = (int)(r % p.Wo); r /= p.Wo;
-    const int y = (int)(r % p.Ho);
-    const int img = (int)(r / p.Ho);
-    const int Wi = p.Wo * 2;
-    const size_t p0 = img * p.in_img + ((size_t)(2 * y) * Wi + 2 * x) * p.in_cs + c * 8;
-    float a[8], bq[8], cq[8], d[8], o[8];
-    load8_any(p.in, p.in_lo, p0, sp, a);
-    load8_any(p.in, p.in_lo, p0 + p.in_cs, sp, bq);
-    load8_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs, sp, cq);
-    load8_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs + p.in_cs, sp, d);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.Wo * p.c4) return;
+  const int x = idx / p.c4, c = idx - x * p.c4;
+  const int y = blockIdx.y, img = blockIdx.z;
+  const int Wi = p.Wo * 2;
+  const size_t p0 = (size_t)img * p.in_img + ((size_t)(2 * y) * Wi + 2 * x) * p.in_cs + c * 8;
+  float a[8], bq[8], cq[8], d[8], o[8];
+  load8_any(p.in, p.in_lo, p0, sp, a);
+  load8_any(p.in, p.in_lo, p0 + p.in_cs, sp, bq);
+  load8_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs, sp, cq);
+  load8_any(p.in, p.in_lo, p0 + (size_t)Wi * p.in_cs + p.in_cs, sp, d);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = (a[k] + bq[k] + cq[k] + d[k]) * 0.25f;
-    store8_any(p.out, p.out_lo, img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + c * 8, o, sp);
-  }
+  for (int k = 0; k < 8; ++k) o[k] = (a[k] + bq[k] + cq[k] + d[k]) * 0.25f;
+  store8_any(p.out, p.out_lo, (size_t)img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + c * 8, o, sp);
 }
 
 // Bilinear align_corners=True upsample (hardnet.py:249-254) of a list of channel slices into one
@@ -532,36 +529,36 @@ struct UpParams {
   float sh, sw;
 };
 
-__global__ void upsample_bilinear_kernel(UpParams p) {
-  const size_t total = (size_t)p.b * p.Ho * p.Wo * p.c4_total;
+// grid = (ceil(Wo * groups / 256), Ho, b): one thread per (output pixel, 8-channel group), 32-bit index math only
+// (the first version's three 64-bit div/mod per thread made the kernel instruction-bound at 1.7 TB/s).
+__global__ void __launch_bounds__(256) upsample_bilinear_kernel(UpParams p) {
   const bool sp = p.split != 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % p.c4_total) * 8;
-    size_t r = i / p.c4_total;
-    const int x = (int)(r % p.Wo); r /= p.Wo;
-    const int y = (int)(r % p.Ho);
-    const int img = (int)(r / p.Ho);
-    const int cout = c;
-    int s = 0;
-    while (c >= p.segs[s].cpad) { c -= p.segs[s].cpad; ++s; }
-    const float fy = p.sh * (float)y, fx = p.sw * (float)x;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const size_t base = img * p.in_img[s] + c;
-    const int cs = p.segs[s].cstride;
-    const void* bh = p.segs[s].base;
-    const void* bl = p.segs[s].base_lo;
-    float v00[8], v01[8], v10[8], v11[8], o[8];
-    load8_any(bh, bl, base + ((size_t)y0 * p.Wi + x0) * cs, sp, v00);
-    load8_any(bh, bl, base + ((size_t)y0 * p.Wi + x1) * cs, sp, v01);
-    load8_any(bh, bl, base + ((size_t)y1 * p.Wi + x0) * cs, sp, v10);
-    load8_any(bh, bl, base + ((size_t)y1 * p.Wi + x1) * cs, sp, v11);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.Wo * p.c4_total) return;
+  const int x = idx / p.c4_total;
+  int c = (idx - x * p.c4_total) * 8;
+  const int y = blockIdx.y, img = blockIdx.z;
+  const int cout = c;
+  int s = 0;
+  while (c >= p.segs[s].cpad) { c -= p.segs[s].cpad; ++s; }
+  const float fy = p.sh * (float)y, fx = p.sw * (float)x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const size_t base = (size_t)img * p.in_img[s] + c;
+  const int cs = p.segs[s].cstride;
+  const void* bh = p.segs[s].base;
+  const void* bl = p.segs[s].base_lo;
+  const int r0 = y0 * p.Wi, r1 = y1 * p.Wi;
+  float v00[8], v01[8], v10[8], v11[8], o[8];
+  load8_any(bh, bl, base + (size_t)(r0 + x0) * cs, sp, v00);
+  load8_any(bh, bl, base + (size_t)(r0 + x1) * cs, sp, v01);
+  load8_any(bh, bl, base + (size_t)(r1 + x0) * cs, sp, v10);
+  load8_any(bh, bl, base + (size_t)(r1 + x1) * cs, sp, v11);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]);
-    store8_any(p.out, p.out_lo, img * p.out_img + ((size_t)y * p.Wo + x) * p.out_cs + cout, o, sp);
-  }
+  for (int k = 0; k < 8; ++k) o[k] = hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]);
+  store8_any(p.out, p.out_lo, (size_t)img * p.out_img + (size_t)(y * p.Wo + x) * p.out_cs + cout, o, sp);
 }
 
 // K5: fused bilinear(align_corners) x4 upsample + argmax (hardnet.py:373-377 + bg_model.py:98).
@@ -627,75 +624,74 @@ __global__ void upsample_argmax_kernel(const float* __restrict__ q, int b, int n
 // Strip variant for the usual x4 case (3*sw < 1, fw % 4 == 0): one thread = 4 consecutive output
 // pixels of a row; they touch at most 3 source columns x 2 rows, loaded once (18 instead of 48 LDG.128).
 // Same interpolation arithmetic as upsample_argmax_kernel (bit-identical logits).
-__global__ void upsample_argmax_strip_kernel(const float* __restrict__ q, int b, int ncls, int h, int w, int fh, int fw,
-                                             float sh, float sw, uint8_t* __restrict__ seg8,
-                                             long long* __restrict__ seg64, float* __restrict__ full) {
-  const int fw4 = fw >> 2;
-  const size_t total = (size_t)b * fh * fw4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int xs = (int)(i % fw4) * 4;
-    size_t r = i / fw4;
-    const int y = (int)(r % fh);
-    const int img = (int)(r / fh);
-    const float fy = sh * (float)y;
-    const int y0 = (int)fy;
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-    const float ly = fy - (float)y0, hy = 1.f - ly;
-    const int c0 = (int)(sw * (float)xs);
-    const int cA = c0, cB = min(c0 + 1, w - 1), cC = min(c0 + 2, w - 1);
-    const float* base = q + (size_t)img * h * w * 16;
-    const float4* p0[3] = {reinterpret_cast<const float4*>(base + ((size_t)y0 * w + cA) * 16),
-                           reinterpret_cast<const float4*>(base + ((size_t)y0 * w + cB) * 16),
-                           reinterpret_cast<const float4*>(base + ((size_t)y0 * w + cC) * 16)};
-    const float4* p1[3] = {reinterpret_cast<const float4*>(base + ((size_t)y1 * w + cA) * 16),
-                           reinterpret_cast<const float4*>(base + ((size_t)y1 * w + cB) * 16),
-                           reinterpret_cast<const float4*>(base + ((size_t)y1 * w + cC) * 16)};
-    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    int arg[4] = {0, 0, 0, 0};
-    int ia[4], ib[4];
-    float lx[4], hx[4];
+template <bool FULL>
+__global__ void __launch_bounds__(256) upsample_argmax_strip_kernel(const float* __restrict__ q, int ncls, int h, int w, int fh, int fw,
+                                                                    float sh, float sw, uint8_t* __restrict__ seg8,
+                                                                    long long* __restrict__ seg64, float* __restrict__ full) {
+  // grid = (ceil(fw / 4 / 256), fh, b): one thread per strip of 4 output pixels, 32-bit index math
+  const int strip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (strip >= (fw >> 2)) return;
+  const int xs = strip * 4, y = blockIdx.y, img = blockIdx.z;
+  const float fy = sh * (float)y;
+  const int y0 = (int)fy;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, hy = 1.f - ly;
+  const int c0 = (int)(sw * (float)xs);
+  const int cA = c0, cB = min(c0 + 1, w - 1), cC = min(c0 + 2, w - 1);
+  const float* base = q + (size_t)img * h * w * 16;
+  const float4* p0[3] = {reinterpret_cast<const float4*>(base + (size_t)(y0 * w + cA) * 16),
+                         reinterpret_cast<const float4*>(base + (size_t)(y0 * w + cB) * 16),
+                         reinterpret_cast<const float4*>(base + (size_t)(y0 * w + cC) * 16)};
+  const float4* p1[3] = {reinterpret_cast<const float4*>(base + (size_t)(y1 * w + cA) * 16),
+                         reinterpret_cast<const float4*>(base + (size_t)(y1 * w + cB) * 16),
+                         reinterpret_cast<const float4*>(base + (size_t)(y1 * w + cC) * 16)};
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int arg[4] = {0, 0, 0, 0};
+  bool a1[4], b1[4], b2[4];
+  float lx[4], hx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float fx = sw * (float)(xs + j);
+    const int x0 = (int)fx;
+    lx[j] = fx - (float)x0; hx[j] = 1.f - lx[j];
+    const int ia = x0 - c0;                                   // 0 or 1: left column of pixel j within {cA, cB, cC}
+    const int ib = ia + (x0 < w - 1 ? 1 : 0);                 // 0..2: right column
+    a1[j] = ia != 0; b1[j] = ib == 1; b2[j] = ib == 2;
+  }
+  const int nq = (ncls + 3) >> 2;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k >= nq) break;
+    float4 t0[3], t1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { t0[c] = __ldg(p0[c] + k); t1[c] = __ldg(p1[c] + k); }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float fx = sw * (float)(xs + j);
-      const int x0 = (int)fx;
-      lx[j] = fx - (float)x0; hx[j] = 1.f - lx[j];
-      ia[j] = x0 - c0;                                   // 0 or 1
-      ib[j] = ia[j] + (x0 < w - 1 ? 1 : 0);              // 0..2 (x1 column)
-    }
-    const int nq = (ncls + 3) >> 2;
+      const float4 a = a1[j] ? t0[1] : t0[0];
+      const float4 b_ = b2[j] ? t0[2] : (b1[j] ? t0[1] : t0[0]);
+      const float4 c_ = a1[j] ? t1[1] : t1[0];
+      const float4 d = b2[j] ? t1[2] : (b1[j] ? t1[1] : t1[0]);
+      float v[4];
+      v[0] = hy * (hx[j] * a.x + lx[j] * b_.x) + ly * (hx[j] * c_.x + lx[j] * d.x);
+      v[1] = hy * (hx[j] * a.y + lx[j] * b_.y) + ly * (hx[j] * c_.y + lx[j] * d.y);
+      v[2] = hy * (hx[j] * a.z + lx[j] * b_.z) + ly * (hx[j] * c_.z + lx[j] * d.z);
+      v[3] = hy * (hx[j] * a.w + lx[j] * b_.w) + ly * (hx[j] * c_.w + lx[j] * d.w);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k >= nq) break;
-      float4 t0[3], t1[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { t0[c] = __ldg(p0[c] + k); t1[c] = __ldg(p1[c] + k); }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 a = ia[j] == 0 ? t0[0] : t0[1];
-        const float4 b_ = ib[j] == 0 ? t0[0] : (ib[j] == 1 ? t0[1] : t0[2]);
-        const float4 c_ = ia[j] == 0 ? t1[0] : t1[1];
-        const float4 d = ib[j] == 0 ? t1[0] : (ib[j] == 1 ? t1[1] : t1[2]);
-        float v[4];
-        v[0] = hy * (hx[j] * a.x + lx[j] * b_.x) + ly * (hx[j] * c_.x + lx[j] * d.x);
-        v[1] = hy * (hx[j] * a.y + lx[j] * b_.y) + ly * (hx[j] * c_.y + lx[j] * d.y);
-        v[2] = hy * (hx[j] * a.z + lx[j] * b_.z) + ly * (hx[j] * c_.z + lx[j] * d.z);
-        v[3] = hy * (hx[j] * a.w + lx[j] * b_.w) + ly * (hx[j] * c_.w + lx[j] * d.w);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = k * 4 + e;
-          if (c < ncls) {
-            if (full) full[(((size_t)img * ncls + c) * fh + y) * fw + xs + j] = v[e];
-            if (v[e] > best[j]) { best[j] = v[e]; arg[j] = c; }
-          }
+      for (int e = 0; e < 4; ++e) {
+        const int c = k * 4 + e;
+        if (c < ncls) {
+          if (FULL) full[(((size_t)img * ncls + c) * fh + y) * fw + xs + j] = v[e];
+          if (v[e] > best[j]) { best[j] = v[e]; arg[j] = c; }
         }
       }
     }
-    const size_t o = ((size_t)img * fh + y) * fw + xs;
-    if (seg8) *reinterpret_cast<uchar4*>(seg8 + o) = make_uchar4((uint8_t)arg[0], (uint8_t)arg[1], (uint8_t)arg[2], (uint8_t)arg[3]);
-    if (seg64) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) seg64[o + j] = arg[j];
-    }
+  }
+  const size_t o = ((size_t)img * fh + y) * fw + xs;
+  if (seg8) *reinterpret_cast<uchar4*>(seg8 + o) = make_uchar4((uint8_t)arg[0], (uint8_t)arg[1], (uint8_t)arg[2], (uint8_t)arg[3]);
+  if (seg64) {
+    longlong2* o64 = reinterpret_cast<longlong2*>(seg64 + o);
+    o64[0] = make_longlong2(arg[0], arg[1]);
+    o64[1] = make_longlong2(arg[2], arg[3]);
   }
 }
 
@@ -1403,8 +1399,7 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         p.out = a.ptr(s.out.buf, s.out.coff); p.out_lo = a.ptr_lo(s.out.buf, s.out.coff); p.out_cs = ob.cstride;
         p.out_img = a.img_elems[s.out.buf];
         p.b = b; p.Ho = H >> ob.shift; p.Wo = W >> ob.shift; p.c4 = in.cpad() / 8; p.split = split;
-        const size_t total = (size_t)b * p.Ho * p.Wo * p.c4;
-        avgpool2_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+        avgpool2_kernel<<<dim3(cdiv(p.Wo * p.c4, 256), p.Ho, b), 256, 0, st>>>(p);
         PF_CHECK_CUDA(cudaGetLastError());
         break;
       }
@@ -1429,8 +1424,7 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         p.c4_total = ctot / 8; p.split = split;
         p.sh = p.Ho > 1 ? (float)(p.Hi - 1) / (float)(p.Ho - 1) : 0.f;
         p.sw = p.Wo > 1 ? (float)(p.Wi - 1) / (float)(p.Wo - 1) : 0.f;
-        const size_t total = (size_t)b * p.Ho * p.Wo * p.c4_total;
-        upsample_bilinear_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+        upsample_bilinear_kernel<<<dim3(cdiv(p.Wo * p.c4_total, 256), p.Ho, b), 256, 0, st>>>(p);
         PF_CHECK_CUDA(cudaGetLastError());
         break;
       }
@@ -1447,9 +1441,15 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         const float sh = final_h > 1 ? (float)(h - 1) / (float)(final_h - 1) : 0.f;
         const float sw = final_w > 1 ? (float)(w - 1) / (float)(final_w - 1) : 0.f;
         const size_t total = (size_t)b * final_h * final_w;
-        if (final_w % 4 == 0 && 3.f * sw < 0.999f && (((size_t)out_seg_u8_dev) & 3) == 0)
-          upsample_argmax_strip_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(
-              q, b, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev, (long long*)out_seg_i64_dev, out_full_dev);
+        if (final_w % 4 == 0 && 3.f * sw < 0.999f && (((size_t)out_seg_u8_dev) & 3) == 0 && (((size_t)out_seg_i64_dev) & 15) == 0) {
+          const dim3 grid(cdiv(final_w / 4, 256), final_h, b);
+          if (out_full_dev)
+            upsample_argmax_strip_kernel<true><<<grid, 256, 0, st>>>(q, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev,
+                                                                    (long long*)out_seg_i64_dev, out_full_dev);
+          else
+            upsample_argmax_strip_kernel<false><<<grid, 256, 0, st>>>(q, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev,
+                                                                     (long long*)out_seg_i64_dev, nullptr);
+        }
         else
           upsample_argmax_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(
               q, b, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev, (long long*)out_seg_i64_dev, out_full_dev);

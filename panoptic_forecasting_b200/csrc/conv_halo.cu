@@ -14,7 +14,8 @@
 // high-resolution layers, where a CTA visits many tiles) or STREAMED per (chunk, tap) through a
 // second mbarrier ring.  The fp32 accumulator is double-buffered in TMEM so the epilogue of tile
 // i overlaps the MMAs of tile i+1.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 epilogue.
+// Warp roles (224 threads): warp 0 TMA producer, warps 1 and 6 MMA issuers (alternate chunks; warp 1 owns TMEM),
+// warps 2..5 epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -28,7 +29,8 @@ namespace pf {
 using namespace tc;
 
 namespace {
-constexpr int kMaxA = 4, kMaxB = 8;
+constexpr int kMaxA = 8, kMaxB = 8;
+constexpr int kHaloThreads = 224;      // warp 0 TMA producer, warps 1 and 6 MMA issuers, warps 2..5 epilogue
 
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
@@ -121,9 +123,17 @@ struct MmaCtx {
   bool dbg;
 };
 
-// The MMA warp's whole life: per tile, per chunk: wait for the staged activations, issue, release the stage.
+// Two MMA warps take alternate chunks.  tcgen05.mma issue is effectively synchronous with the tensor pipe (a
+// ~100-cycle pause of the issuing thread idles the pipe for ~100 cycles: measured), so everything that is not
+// an MMA -- mbarrier waits, fences, descriptor set-up, the commits -- has to happen in ANOTHER warp while this
+// one issues.  Each warp prepares its next chunk, then waits for its turn on a named barrier; the turn passes
+// right after the other warp's last MMA of the previous chunk, which keeps the issue order (and so the
+// accumulation order) identical to a single issuing warp.
+__device__ __forceinline__ void turn_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void turn_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
 template <int KS, bool RES>
-__device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& m) {
+__device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& m, const int role) {
   const uint32_t el = m.el;
   const int SA = L.stages_a, nchunk = L.nchunk, ntile = L.ntile;
   const uint32_t full_a0 = m.bar0, empty_a0 = m.bar0 + 8u * kMaxA;
@@ -133,42 +143,53 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
   ci.smem_base = m.smem_base; ci.ntile4 = (uint32_t)ntile * 4u;
   ci.b_base = m.b_base; ci.b_tile = m.b_tile;
   ci.bar_full_b0 = m.bar0 + 8u * (2 * kMaxA); ci.bar_empty_b0 = m.bar0 + 8u * (2 * kMaxA + kMaxB); ci.SB = L.stages_b;
+  const int my_tiles = (m.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int last_ia = my_tiles * nchunk - 1;
   int ia = 0, ib = 0, st = 0, acc = 0;
   uint32_t ph_a = 0, ph_t = 1;
   long long wait_full = 0, wait_tmem = 0, w0 = 0;
-  uint32_t code = L.chunk[0];
-  for (int t = blockIdx.x; t < m.total_tiles; t += gridDim.x) {
-    if (m.dbg) w0 = clock64();
-    mbar_wait(tmem_empty0 + 8u * acc, ph_t);
-    if (m.dbg) wait_tmem += clock64() - w0;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    ci.d = m.tmem_d + (uint32_t)(acc * 2 * ntile);
-    uint32_t woff = 0, accf = 0;
-    for (int j = 0; j < nchunk; ++j, ++ia) {
-      const uint32_t next = L.chunk[j + 1 == nchunk ? 0 : j + 1];     // fetched while this chunk's MMAs issue
-      if (m.dbg) w0 = clock64();
-      mbar_wait(full_a0 + 8u * st, ph_a);
-      if (m.dbg) wait_full += clock64() - w0;
-      if (m.dbg && el && ia == 0) L.dbg_ts[3] = clock64();
-      if (m.dbg && el && ia < 24) L.dbg_ts[40 + ia] = clock64();
+  const bool dbg = m.dbg && role == 0;
+  for (int tl = 0; tl < my_tiles; ++tl) {
+    if ((ia & 1) == role) {                   // owner of the tile's first chunk: the accumulator buffer must be drained
+      if (dbg) w0 = clock64();
+      mbar_wait(tmem_empty0 + 8u * acc, ph_t);
+      if (dbg) wait_tmem += clock64() - w0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      ci.sa = m.a_base + st * 2 * m.a_tile;
-      issue_dispatch<KS, RES>(code, ci, accf, woff, ib);
-      accf = 1u;
-      if (m.dbg && el && ia < 24) L.dbg_ts[64 + ia] = clock64();
-      umma_commit_p(empty_a0 + 8u * st, el);
-      if (++st == SA) { st = 0; ph_a ^= 1u; }
-      code = next;
     }
-    umma_commit_p(tmem_full0 + 8u * acc, el);
-    if (m.dbg && el && t == (int)blockIdx.x) L.dbg_ts[4] = clock64();
+    ci.d = m.tmem_d + (uint32_t)(acc * 2 * ntile);
+    uint32_t woff = 0;
+    for (int j = 0; j < nchunk; ++j, ++ia) {
+      const uint32_t code = L.chunk[j];
+      if ((ia & 1) == role) {
+        if (dbg) w0 = clock64();
+        mbar_wait(full_a0 + 8u * st, ph_a);
+        if (dbg) wait_full += clock64() - w0;
+        if (dbg && el && ia == 0) L.dbg_ts[3] = clock64();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        ci.sa = m.a_base + st * 2 * m.a_tile;
+        if (ia > 0) turn_wait(1 + role);
+        if (dbg && el && ia < 48) L.dbg_ts[40 + (ia >> 1)] = clock64();
+        issue_dispatch<KS, RES>(code, ci, j == 0 ? 0u : 1u, woff, ib);
+        if (ia < last_ia) turn_pass(2 - role);
+        if (dbg && el && ia < 48) L.dbg_ts[64 + (ia >> 1)] = clock64();
+        umma_commit_p(empty_a0 + 8u * st, el);
+        if (j + 2 >= nchunk) umma_commit_p(tmem_full0 + 8u * acc, el);     // this warp's last chunk of the tile
+        if (dbg && el && tl == 0 && j + 1 == nchunk) L.dbg_ts[4] = clock64();
+      } else {
+        // the other warp's chunk: keep the weight cursor / ring counters in step
+        const uint32_t w = code & 0xFFu;
+        if (RES) woff += (uint32_t)(KS * KS) * align1k(ci.ntile4 * w);
+        else ib += KS * KS;
+      }
+      if (++st == SA) { st = 0; ph_a ^= 1u; }
+    }
     if (acc) ph_t ^= 1u;
     acc ^= 1;
   }
-  if (m.dbg && el) { L.dbg_ts[7] = clock64(); L.dbg_ts[9] = wait_full; L.dbg_ts[10] = wait_tmem; }
+  if (dbg && el) { L.dbg_ts[7] = clock64(); L.dbg_ts[9] = wait_full; L.dbg_ts[10] = wait_tmem; }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxB + 5];
   __shared__ uint32_t tmem_base_smem;
@@ -203,7 +224,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
     for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
     mbar_init(wbar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
+    // both MMA warps commit to tmem_full after their last chunk of a tile (a commit only covers the issuing thread's MMAs)
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), L.nchunk >= 2 ? 2 : 1); mbar_init(tmem_empty(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -292,8 +314,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
       }
       if (dbg && el) L.dbg_ts[11] = wait_acc;
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform loops, one elected lane issues) =====
+  } else if (warp == 1 || warp == 6) {
+    // ===== MMA issuers (warp-uniform loops, one elected lane issues; alternate chunks, see mma_warp_loop) =====
+    const int role = warp == 1 ? 0 : 1;
     const uint32_t el = elect_one();
     {
       // kind::f16, bf16 x bf16 -> fp32, M = 128.  Two MMAs per 16-channel K atom:
@@ -305,20 +328,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
       const uint32_t idesc1 = idesc_base | ((uint32_t)(ntile >> 3) << 17);
       const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * ntile) >> 3) << 17);
       if (L.resident) mbar_wait(wbar, 0);
-      if (dbg && el) L.dbg_ts[2] = clock64();
+      if (dbg && el && role == 0) L.dbg_ts[2] = clock64();
       MmaCtx mc;
       mc.el = el; mc.tmem_d = tmem_d; mc.smem_base = smem_base; mc.a_base = a_base; mc.a_tile = a_tile;
       mc.b_base = b_base; mc.b_tile = b_tile; mc.bar0 = bar0; mc.total_tiles = total_tiles; mc.dbg = dbg;
       mc.idesc1 = idesc1; mc.idesc2 = idesc2;
       const int ks = NT == 1 ? 1 : (L.tap_mask == 0x1FF ? 3 : 2);
       if (L.resident) {
-        if (ks == 3) mma_warp_loop<3, true>(L, mc);
-        else if (ks == 1) mma_warp_loop<1, true>(L, mc);
-        else mma_warp_loop<2, true>(L, mc);
+        if (ks == 3) mma_warp_loop<3, true>(L, mc, role);
+        else if (ks == 1) mma_warp_loop<1, true>(L, mc, role);
+        else mma_warp_loop<2, true>(L, mc, role);
       } else {
-        if (ks == 3) mma_warp_loop<3, false>(L, mc);
-        else if (ks == 1) mma_warp_loop<1, false>(L, mc);
-        else mma_warp_loop<2, false>(L, mc);
+        if (ks == 3) mma_warp_loop<3, false>(L, mc, role);
+        else if (ks == 1) mma_warp_loop<1, false>(L, mc, role);
+        else mma_warp_loop<2, false>(L, mc, role);
       }
     }
     __syncwarp();
@@ -328,6 +351,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
     const int m = q * 32 + lane;
     int tc_ = 0;
     long long wait_epi = 0, w0 = 0;
+    float bias_r[2][16];                 // bias of the CTA's channels when the whole N tile fits two register groups
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bias_r[g][i] = (ntile <= 32 && g * 16 < ntile && n0 + g * 16 < L.cout_store) ? __ldg(L.bias + n0 + g * 16 + i) : 0.f;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
       const int acc = tc_ & 1;
       const int img = t / tiles_per_img;
@@ -356,14 +384,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
         a00 = ab + ((size_t)ay0 * L.add_W + ax0) * L.add_cs; a01 = ab + ((size_t)ay0 * L.add_W + ax1) * L.add_cs;
         a10 = ab + ((size_t)ay1 * L.add_W + ax0) * L.add_cs; a11 = ab + ((size_t)ay1 * L.add_W + ax1) * L.add_cs;
       }
-      for (int c = 0; c < ntile; c += 16) {
-        const int n = n0 + c;
-        if (n >= L.cout_store) break;
-        float v[16], v2[16];
-        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * ntile + c), v);
-        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * ntile + ntile + c), v2);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (v[i] + v2[i]) + __ldg(L.bias + n + i);
+      const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * ntile);
+      // the accumulator buffer goes back to the MMA warps as soon as it has been READ (not after the stores):
+      // with only two buffers the MMAs of tile i+2 otherwise wait for the whole epilogue of tile i
+      auto release = [&]() {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(acc));
+      };
+      auto finish16 = [&](float (&v)[16], const int n) {     // v = conv + bias of channels [n, n + 16)
         if (a00) {
           const float ahy = 1.f - aly, ahx = 1.f - alx;
 #pragma unroll
@@ -380,12 +409,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (!inside || (L.dbg_mode & 2)) continue;
+        if (!inside || (L.dbg_mode & 2)) return;
         if (L.out_f32) {
           float4* o = reinterpret_cast<float4*>(L.out_f32 + pix + n);
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          continue;
+          return;
         }
         uint4 h[2], l[2];
         uint2 th, tl;
@@ -399,11 +428,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const HaloLayer 
         uint4* ol = reinterpret_cast<uint4*>(L.out_lo + pix + n);
         oh[0] = h[0]; oh[1] = h[1];
         ol[0] = l[0]; ol[1] = l[1];
+      };
+      if (ntile <= 32) {
+        // whole accumulator row in registers (2 or 4 loads in flight), buffer released, then the math and the stores
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        const bool two = ntile == 32 && n0 + 16 < L.cout_store;
+        tmem_ld16_nowait(trow, r0);
+        tmem_ld16_nowait(trow + (uint32_t)ntile, r1);
+        if (two) {
+          tmem_ld16_nowait(trow + 16u, r2);
+          tmem_ld16_nowait(trow + (uint32_t)ntile + 16u, r3);
+        }
+        tmem_ld_wait16(r0); tmem_ld_wait16(r1);
+        if (two) { tmem_ld_wait16(r2); tmem_ld_wait16(r3); }
+        release();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + bias_r[0][i];
+        finish16(v, n0);
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + bias_r[1][i];
+          finish16(v, n0 + 16);
+        }
+      } else {
+        int ngroups = 0;
+        for (int c = 0; c < ntile && n0 + c < L.cout_store; c += 16) ++ngroups;
+        for (int g = 0; g < ngroups; ++g) {
+          const int c = g * 16, n = n0 + c;
+          float v[16], v2[16];
+          tmem_ld16(trow + (uint32_t)c, v);
+          tmem_ld16(trow + (uint32_t)(ntile + c), v2);
+          if (g == ngroups - 1) release();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (v[i] + v2[i]) + __ldg(L.bias + n + i);
+          finish16(v, n);
+        }
+        if (ngroups == 0) release();
       }
-      // accumulator drained -> hand the TMEM buffer back to the MMA warp
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty(acc));
       if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[6] = clock64();
     }
     if (dbg && threadIdx.x == 64) L.dbg_ts[12] = wait_epi;
@@ -501,7 +563,10 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
     L->w_bytes_total = (uint32_t)w_total;
     L->w_tx_total = (uint32_t)w_tx;
     int sa = (int)((budget - w_total) / (2 * a_tile));
-    L->stages_a = sa > kMaxA ? kMaxA : sa;
+    // ring depth: 4 stages, 8 for the 16-channel chunks (12 KB per stage: with 4 the bytes in flight per SM are too
+    // few to cover the DRAM latency -- base.1 went 312 -> 255 us; deeper rings made the wider layers slower)
+    const int cap = 2 * a_tile <= 12 * 1024 ? kMaxA : 4;
+    L->stages_a = sa > cap ? cap : sa;
     L->stages_b = 1;
     *smem_bytes = w_total + (size_t)L->stages_a * 2 * a_tile + 1024;
     return true;
@@ -532,7 +597,7 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   if (use_pdl < 0) { const char* e = getenv("PF_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, nblocks);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kHaloThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr_pdl[1];
