@@ -18,7 +18,7 @@ sd = synthetic.make_bg_state_dict({k: v.cpu() for k, v in m.state_dict().items()
 m.load_state_dict(sd)
 m._upload(torch.device("cuda", 0))
 info = _lib.ConvInfo()
-shapes = {1: (512, 1024), 3: (256, 512), 7: (256, 512), 8: (256, 512), 13: (128, 256), 23: (64, 128), 43: (16, 32), 76: (256, 512), 72: (256, 512)}
+shapes = {1: (512, 1024), 3: (256, 512), 7: (256, 512), 8: (256, 512), 13: (128, 256), 23: (64, 128), 43: (16, 32), 76: (256, 512), 72: (256, 512), 66: (128, 256), 56: (64, 128), 14: (128, 256), 70: (128, 256), 68: (128, 256)}
 for i in [int(a) for a in sys.argv[1:]] or sorted(shapes):
     L.pf_bgnet_conv_info(m._net, i, C.byref(info))
     H, W = shapes.get(i, (256, 512))
