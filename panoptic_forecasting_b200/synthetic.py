@@ -170,3 +170,44 @@ def make_bg_state_dict(ref_state_dict_like, seed=0):
         else:
             raise KeyError(k)
     return out
+
+
+def make_merge_inputs(b, n_per_item, h, w, seed=0, use_bbox_ulbr=True, mask_size=28):
+    """Synthetic inputs of the fg -> bg panoptic merge (fg_model.py:515-588): per batch item a piecewise-constant
+    background label map (ids 0..18, so the `>= 11 -> 255` rule fires), a background depth map with an invalid
+    band, and `n` instances (blob-shaped mask logits, boxes that overlap each other and the image border,
+    classes 0..7, depths straddling the background's).  numpy only; lists indexed by batch item."""
+    rng = np.random.RandomState(seed)
+    out = {k: [] for k in ("background", "bg_depth", "bg_depth_mask", "mask_logits", "bboxes", "classes", "depths")}
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    my, mx = np.mgrid[0:mask_size, 0:mask_size].astype(np.float32)
+    for i in range(b):
+        n = int(n_per_item[i])
+        bg = ((yy // max(1, h // 6)).astype(np.int64) * 3 + (xx // max(1, w // 8)).astype(np.int64)) % 19
+        out["background"].append(bg.astype(np.int64))
+        depth = (8.0 + 60.0 * (1.0 - yy / h) + 5.0 * np.sin(xx / w * 12.0)).astype(np.float32)
+        out["bg_depth"].append(depth)
+        mask = np.ones((h, w), dtype=bool)
+        mask[h // 3: h // 3 + max(1, h // 16), :] = False
+        mask[:, w // 5: w // 5 + max(1, w // 32)] &= rng.rand(h, 1) > 0.5
+        out["bg_depth_mask"].append(mask)
+        cx = rng.uniform(0.0, w, n)
+        cy = rng.uniform(0.2 * h, 0.9 * h, n)
+        bw = rng.uniform(0.04 * w, 0.3 * w, n)
+        bh = rng.uniform(0.08 * h, 0.5 * h, n)
+        if n >= 2:                                   # force one heavy overlap
+            cx[1], cy[1] = cx[0] + 0.2 * bw[0], cy[0] + 0.1 * bh[0]
+        if use_bbox_ulbr:
+            boxes = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+        else:
+            boxes = np.stack([cx, cy, bw, bh], 1)
+        out["bboxes"].append(boxes.astype(np.float32))
+        logits = np.empty((n, mask_size, mask_size), dtype=np.float32)
+        for k in range(n):
+            r = rng.uniform(0.25, 0.55) * mask_size
+            oy, ox = rng.uniform(0.35, 0.65, 2) * mask_size
+            logits[k] = 6.0 * (1.0 - np.sqrt((my - oy) ** 2 + (mx - ox) ** 2) / r) + rng.normal(0, 0.7, (mask_size, mask_size))
+        out["mask_logits"].append(logits)
+        out["classes"].append(rng.randint(0, 8, n).astype(np.int64))
+        out["depths"].append(rng.uniform(5.0, 70.0, n).astype(np.float32))
+    return out
