@@ -174,19 +174,30 @@ int pf_upsample_argmax(const float* logits_nchw_dev, int b, int classes, int h, 
  * Replaces the per-instance paste + z-test loop of FGModel.predict_panoptic
  * (panoptic_forecasting/models/fg/fg_model.py:515-518, 557-588) and model_utils.paste_mask
  * (panoptic_forecasting/models/fg/model_utils.py:30-57; bilinear grid_sample, align_corners=False, zeros).
- * Instances of all batch items are concatenated IN PAINT ORDER (the reference paints far-to-near: depth sorted
- * descending when use_depth_sorting); item i owns instances [inst_begin[i], inst_begin[i+1]).  seg_vals[k] is
- * the panoptic id painted by instance k ((class + 11) * 1000 + running index of that class, fg_model.py:576-577).
- *   background      int64 [b,H,W] or NULL (all 255); ids >= 11 become 255 (:517)
+ * Instances of all batch items are concatenated; item i owns [inst_begin[i], inst_begin[i+1]).
+ *
+ * pf_panoptic_paint_order (fg_model.py:560-577): per item, order[k] = index (into the concatenated arrays) of
+ * the k-th painted instance -- depth descending (far to near, stable, NaN first) when depths is given, index
+ * order when it is NULL -- and seg_vals[k] = the panoptic id that instance paints,
+ * (class + 11) * 1000 + number of earlier painted instances of the same class (:576-577).
+ *   classes int64 [n]; depths f32 [n] or NULL; inst_begin int32 [b+1]; outputs int32 [n]. */
+int pf_panoptic_paint_order(const int64_t* classes_dev, const float* depths_dev, const int32_t* inst_begin_dev,
+                            int b, int32_t* order_dev, int32_t* seg_vals_dev, void* stream);
+
+/* pf_panoptic_merge (:515-518, :557-588): one pass over the frame.
+ *   background      int64 [b,H,W] (uint8 if background_is_u8), or NULL (all 255); ids >= 11 become 255 (:517)
  *   bg_depth        f32 [b,H,W] or NULL; bg_depth_mask u8 [b,H,W] or NULL (0 => depth 1e9, :567)
  *   masks           f32 [n, mh, mw] mask probabilities (after the sigmoid, :541)
- *   boxes           f32 [n,4]: (x0,y0,x1,y1) if use_bbox_ulbr else (cx,cy,w,h)
+ *   boxes           f32 [n,4] (16-byte aligned): (x0,y0,x1,y1) if use_bbox_ulbr else (cx,cy,w,h)
  *   depths          f32 [n] or NULL.  The z-test (:583-586) runs iff depths and bg_depth are both given.
+ *   seg_vals        int32 [n] indexed by PAINT POSITION; order int32 [n] paint position -> instance index,
+ *                   or NULL when masks/boxes/depths are already stored in paint order.
  * Output int64 [b,H,W].  Bit-identical to the reference's CPU result (same float32 operation order). */
-int pf_panoptic_merge(const int64_t* background_dev, const float* bg_depth_dev, const uint8_t* bg_depth_mask_dev,
-                      const float* masks_dev, const float* boxes_dev, const float* depths_dev,
-                      const int32_t* seg_vals_dev, const int32_t* inst_begin_dev, int b, int H, int W, int mh,
-                      int mw, int use_bbox_ulbr, int64_t* out_seg_dev, void* stream);
+int pf_panoptic_merge(const void* background_dev, int background_is_u8, const float* bg_depth_dev,
+                      const uint8_t* bg_depth_mask_dev, const float* masks_dev, const float* boxes_dev,
+                      const float* depths_dev, const int32_t* seg_vals_dev, const int32_t* order_dev,
+                      const int32_t* inst_begin_dev, int b, int H, int W, int mh, int mw, int use_bbox_ulbr,
+                      int64_t* out_seg_dev, void* stream);
 
 #ifdef __cplusplus
 }

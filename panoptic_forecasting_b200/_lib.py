@@ -48,7 +48,8 @@ SIGNATURES = {
     "pf_bgnet_read_profile": (_i, [_vp, C.POINTER(_f), _i]),
     "pf_bgnet_debug_conv": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "pf_upsample_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "pf_panoptic_merge": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pf_panoptic_paint_order": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "pf_panoptic_merge": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 

@@ -83,7 +83,7 @@ def test_paste_mask_bit_exact_vs_live_reference():
 
 
 def test_abi_symbol_exported(pf_lib):
-    assert hasattr(pf_lib, "pf_panoptic_merge")
+    assert hasattr(pf_lib, "pf_panoptic_merge") and hasattr(pf_lib, "pf_panoptic_paint_order")
 
 
 # ---------------------------------------------------------------------------------------------- GPU
@@ -124,6 +124,52 @@ def test_cuda_merge_matches_oracle_ragged(seed, n, ulbr, zsort):
                                  bg_depth_mask=case["bg_depth_mask"][i] if zsort else None, use_depth_sorting=zsort,
                                  use_bbox_ulbr=ulbr)
         assert np.array_equal(out[i], ref), (i, int((out[i] != ref).sum()))
+
+
+@pytest.mark.gpu
+def test_cuda_paint_order_matches_oracle():
+    """Depth-descending stable order with ties, per-class running ids, ragged items incl. an empty one."""
+    from panoptic_forecasting_b200 import panoptic
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rng = np.random.RandomState(3)
+    ns = (5, 0, 200, 1)
+    classes = [rng.randint(0, 8, n).astype(np.int64) for n in ns]
+    depths = [np.round(rng.uniform(5, 70, n), 0).astype(np.float32) for n in ns]       # rounding forces ties
+    masks = [torch.zeros(n, 28, 28, device=dev) for n in ns]
+    boxes = [torch.zeros(n, 4, device=dev) for n in ns]
+    for zsort in (True, False):
+        prep = panoptic.prepare_instances(masks, boxes, [torch.from_numpy(c).to(dev) for c in classes],
+                                          [torch.from_numpy(d).to(dev) for d in depths] if zsort else None, zsort)
+        vals, order, begin = prep[3].cpu().numpy(), prep[4].cpu().numpy(), prep[5].cpu().numpy()
+        assert list(begin) == [0, 5, 5, 205, 206]
+        for i, n in enumerate(ns):
+            ref_order, ref_vals = merge_oracle.paint_order(classes[i], depths[i] if zsort else None, zsort)
+            assert list(order[begin[i]:begin[i + 1]] - begin[i]) == [int(k) for k in ref_order]
+            assert list(vals[begin[i]:begin[i + 1]]) == ref_vals
+
+
+@pytest.mark.gpu
+def test_cuda_merge_uint8_background_and_odd_width():
+    """uint8 label map straight from the bg exporter; W not a multiple of 4 (scalar load/store path)."""
+    from panoptic_forecasting_b200 import panoptic
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    for h, w in ((64, 256), (50, 131)):
+        n = (6, 2)
+        case = synthetic.make_merge_inputs(len(n), n, h, w, seed=21)
+        probs = [torch.sigmoid(torch.from_numpy(l)).numpy() for l in case["mask_logits"]]
+        bg = torch.stack([t(x) for x in case["background"]])
+        kwargs = dict(pred_bboxes=[t(x) for x in case["bboxes"]], orig_classes=[t(c) for c in case["classes"]],
+                      pred_depths=[t(d) for d in case["depths"]],
+                      background_depths=torch.stack([t(x) for x in case["bg_depth"]]),
+                      background_depth_masks=torch.stack([t(x) for x in case["bg_depth_mask"]]))
+        a = panoptic.merge_instances([t(m) for m in probs], background=bg, **kwargs)["seg"]
+        c = panoptic.merge_instances([t(m) for m in probs], background=bg.to(torch.uint8), **kwargs)["seg"]
+        assert torch.equal(a, c)
+        for i in range(len(n)):
+            ref = merge_oracle.merge(case["background"][i], probs[i], case["bboxes"][i], case["classes"][i], case["depths"][i],
+                                     bg_depth=case["bg_depth"][i], bg_depth_mask=case["bg_depth_mask"][i])
+            assert np.array_equal(a[i].cpu().numpy(), ref), (h, w, i)
 
 
 @pytest.mark.gpu

@@ -51,6 +51,19 @@ def main():
         kms.append(e0.elapsed_time(e1))
     kms = float(np.median(kms))
     assert torch.equal(out, out2)
+    bg8 = args["background"].to(torch.uint8)
+    k8 = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out3 = panoptic.merge_prepared(prepared, b, bg8, args["background_depths"], bgm)
+        e1.record()
+        torch.cuda.synchronize()
+        k8.append(e0.elapsed_time(e1))
+    k8 = float(np.median(k8))
+    assert torch.equal(out, out3)
+    print("pf_panoptic_merge kernel, uint8 background: %.3f ms -> %.0f GB/s of 14 B/px" % (k8, b * H * W * 14 / k8 / 1e6))
     algo = b * H * W * (8 + 4 + 1 + 8)
     print("pf_panoptic_merge kernel alone: %.3f ms -> %.0f frames/s, %.0f GB/s (HBM peak 6556)" % (kms, b / kms * 1e3, algo / kms / 1e6))
     print("pf_panoptic_merge (wrapper incl. order/ids): batch %d x %d instances: %.3f ms  -> %.0f frames/s, %.0f GB/s of %d MB algorithmic"
