@@ -100,6 +100,21 @@ class BGForecastPipeline:
         out['warped_seg'], out['warped_depth'], out['warped_mask'] = seg, d, m
         return out
 
+    def forecast_panoptic(self, inputs, mask_preds, pred_bboxes, orig_classes, pred_depths=None,
+                          background_depths=None, background_depth_masks=None, use_depth_sorting=True,
+                          use_bbox_ulbr=True):
+        """bg forecast followed by the fg -> bg merge of `FGModel.predict_panoptic` (fg_model.py:515-518,557-588),
+        both on the device: the label map never leaves HBM (the reference writes it to a PNG that FGSceneDataset
+        reads back, fg_scene_dataset.py:501-510).  The instance arguments are the forecaster's outputs as in
+        `panoptic.merge_instances`.  Returns the forecast dict plus 'panoptic' int64 [b, H, W]."""
+        from . import panoptic
+        out = self.forecast(inputs)
+        out['panoptic'] = panoptic.merge_instances(
+            mask_preds, pred_bboxes, orig_classes, pred_depths, background=out['seg'],
+            background_depths=background_depths, background_depth_masks=background_depth_masks,
+            use_depth_sorting=use_depth_sorting, use_bbox_ulbr=use_bbox_ulbr)['seg']
+        return out
+
 
 class PipelinedForecaster:
     """Host-buffer front end for throughput runs: uploads of batch i+1 (copy stream) overlap the

@@ -76,3 +76,30 @@ def test_pipelined_forecaster_equals_direct(pf_lib, bg_shapes):
     got.append(pf.collect().clone())
     for i in range(5):
         assert torch.equal(got[i], direct[i % 3])
+
+
+def test_forecast_panoptic_matches_merge_oracle(pf_lib, bg_shapes):
+    """bg forecast -> fg merge on the device (BASELINE config 5's per-item work): the panoptic map equals the merge
+    oracle applied to the bg path's own label map."""
+    from oracle import panoptic_merge_oracle as merge_oracle
+    h, w = 128, 256
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=6)
+    p = bg_params(return_logits=False, seg_dtype="uint8")
+    p["model"]["final_h"], p["model"]["final_w"] = h, w
+    bg = build_model(dict(p, no_gpu=False)).eval()
+    bg.load_state_dict(sd)
+    pipe = BGForecastPipeline(bg)
+    d = synthetic.make_pc_inputs(b=2, t=3, h=h, w=w, dist="R", seed=2)
+    case = synthetic.make_merge_inputs(2, (5, 3), h, w, seed=2)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    probs = [torch.sigmoid(torch.from_numpy(l)) for l in case["mask_logits"]]
+    out = pipe.forecast_panoptic({k: v.cuda() for k, v in d.items()}, [m.cuda() for m in probs],
+                                 [t(x) for x in case["bboxes"]], [t(c) for c in case["classes"]],
+                                 [t(x) for x in case["depths"]])
+    assert out["seg"].dtype == torch.uint8 and out["panoptic"].dtype == torch.int64
+    seg = out["seg"].cpu().numpy()
+    for i in range(2):
+        ref = merge_oracle.merge(seg[i].astype(np.int64), probs[i].numpy(), case["bboxes"][i], case["classes"][i],
+                                 case["depths"][i])
+        assert np.array_equal(out["panoptic"][i].cpu().numpy(), ref)
+    assert (out["panoptic"] >= 11000).any() and (out["panoptic"] < 11).any()
