@@ -364,27 +364,42 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
     }
   }
   // tables while the boxes are in flight
-  for (int i = tid; i < tab_floats; i += blockDim.x) lut[i] = p.tab[i];
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.tab);     // every table is a multiple of 16 floats
+    float4* dst = reinterpret_cast<float4*>(lut);
+    for (int i = tid; i < tab_floats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
   __syncthreads();                 // barrier initialised / tables visible
   tc::mbar_wait(bar_a, 0);
   // in-place conversion: label -> table row (ncls = zero row for padding and ids >= num_classes),
   // depth -> (d - mean) / std * mask (bg_model.py:50-51,67-68), 0 outside the image
-  for (int i = tid; i < p.t * F_IH * F_IW; i += blockDim.x) {
-    const int f = i / (F_IH * F_IW);
-    const int r = i - f * (F_IH * F_IW);
-    const int hy = r / F_IW, hx = r - hy * F_IW;
-    const int iy = iy0 + hy, ix = ix0 + hx;
-    const bool inb = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-    const int li = f * F_LFRAME + hy * F_LPITCH + hx + F_LOFF, di = f * F_DFRAME + hy * F_DPITCH + hx + F_DOFF;
-    const uint8_t lv = lab[li];
-    lab[li] = (inb && lv < p.ncls) ? lv : (uint8_t)p.ncls;
-    if (p.use_depth) {
-      float d = 0.f;
-      if (inb) {
-        const float v = __fdiv_rn(__fadd_rn(dn[di], -p.mean), p.std);
-        d = msk[li] ? v : __fmul_rn(v, 0.0f);
+  // One warp per staged row (uniform frame / row / row-in-bounds), lanes over its 65 columns; the depth is
+  // normalised with a multiply by 1/std (Stage B is a float path: 1 ulp of the input is far inside its tolerance).
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const float inv_std = __fdiv_rn(1.0f, p.std);
+    for (int row = warp; row < p.t * F_IH; row += (F_TH * F_TW) / 32) {
+      const int f = row / F_IH, hy = row - f * F_IH;
+      const int iy = iy0 + hy;
+      const bool rowin = iy >= 0 && iy < p.H;
+      uint8_t* lrow = lab + f * F_LFRAME + hy * F_LPITCH + F_LOFF;
+      const uint8_t* mrow = msk + f * F_LFRAME + hy * F_LPITCH + F_LOFF;
+      float* drow = dn + f * F_DFRAME + hy * F_DPITCH + F_DOFF;
+#pragma unroll
+      for (int hx = lane; hx < F_IW; hx += 32) {
+        const int ix = ix0 + hx;
+        const bool inb = rowin && ix >= 0 && ix < p.W;
+        const uint8_t lv = lrow[hx];
+        lrow[hx] = (inb && lv < p.ncls) ? lv : (uint8_t)p.ncls;
+        if (p.use_depth) {
+          float d = 0.f;
+          if (inb) {
+            const float v = __fmul_rn(__fadd_rn(drow[hx], -p.mean), inv_std);
+            d = mrow[hx] ? v : __fmul_rn(v, 0.0f);
+          }
+          drow[hx] = d;
+        }
       }
-      dn[di] = d;
     }
   }
   __syncthreads();
