@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="target frames per step (the reference export uses batch_size 2)")
+    ap.add_argument("--batch", type=int, default=16, help="target frames per step (the reference export uses batch_size 2)")
     ap.add_argument("--precision", default=os.environ.get("PF_PRECISION", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--dist", default="R", choices=["R", "U"])
     ap.add_argument("--nsets", type=int, default=3)
