@@ -1017,7 +1017,23 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     }
     kb += taps * cp;
   }
-  if (!halo_plan_smem(L, smem)) return 1;
+  // dx-folded form (conv_halo.cu, issue_chunk_fold): full 3x3 layers with at most 32 output channels per CTA
+  const char* nf = getenv("PF_HALO_NO_FOLD");
+  const bool no_fold = nf && nf[0] == '1';
+  // Measured on B200 (batch 8, 1/4 resolution): 58->18 167 -> 115 us, 76->28 230 -> 145 us, 73->18 181 -> 118 us, but
+  // 18->10 58 -> 71 us and 16->24 256 -> 378 us: with a single 16/32-channel chunk a tile is a dozen MMAs and the
+  // epilogue / stores bound it, where the folded form's 8 x 14 tiles (12.5% idle accumulator rows) only cost.
+  int kin = 0;
+  for (int s = seg0; s < seg1; ++s) kin += c.in[s].cpad();
+  const char* ff = getenv("PF_HALO_FOLD_MIN_K");
+  const int fold_min_k = ff && ff[0] ? atoi(ff) : 48;
+  L->fold = (!no_fold && c.ksize == 3 && L->tap_mask == 0x1FF && ntile <= 32 && kin >= fold_min_k) ? 1 : 0;
+  if (L->fold) { L->hx = 16; L->hy = 10; }
+  if (!halo_plan_smem(L, smem)) {
+    if (!L->fold) return 1;
+    L->fold = 0; L->hx = 10; L->hy = 18;
+    if (!halo_plan_smem(L, smem)) return 1;
+  }
   for (int s = seg0; s < seg1; ++s) {
     const int k = s - seg0;
     L->seg_map[k] = (int)maps->size();
@@ -1047,8 +1063,9 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   *nblocks = nb;
   L->Hout = io.Hout; L->Wout = io.Wout; L->batch = io.b;
   L->tiles_x = cdiv(io.Wout, 8); L->tiles_y = cdiv(io.Hout, 16);
+  if (L->fold) { L->tiles_x = cdiv(io.Wout, 14); L->tiles_y = cdiv(io.Hout, 8); }
   int tcols = 32;
-  while (tcols < 4 * ntile) tcols <<= 1;
+  while (tcols < (L->fold ? 12 : 4) * ntile) tcols <<= 1;
   L->tmem_cols = tcols;
   L->cout_store = (io.out_f32 && i == net->final_conv) ? 16 : (c.s2d_out ? 32 : padc(c.cout));
   L->relu = c.relu ? 1 : 0;

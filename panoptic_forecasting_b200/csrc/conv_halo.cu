@@ -117,6 +117,46 @@ __device__ __forceinline__ void issue_dispatch(uint32_t code, const ChunkIssue& 
   }
 }
 
+// dx-folded 3x3 chunk (HaloLayer::fold): the three taps of a filter row share ONE pair of MMAs.  The box is
+// 10 rows x 16 columns, accumulator row m = box pixel (m >> 4, m & 15) shifted down by dy rows (contiguous:
+// SBO = 8 rows), and the B tile of (chunk, dy) stacks the dx = 0,1,2 weight rows: [hi0; hi1; hi2; lo0; lo1; lo2].
+//   D'[:, 0:6n] += A_hi(dy) * B^T (N = 6n)      D'[:, 0:3n] += A_lo(dy) * [hi0; hi1; hi2]^T (N = 3n)
+// D'[(y, x'), dx block] is the contribution of input column x' to output column x' + 1 - dx; the epilogue adds the
+// three blocks with a one-lane shift.  6 instead of 18 A fetches per K atom: for n = 16 an MMA pair costs
+// 56 + 44 cycles (N = 96 / 48) where three pairs cost 3 x (40 + 39).
+template <int W, int NK>
+__device__ __forceinline__ void issue_chunk_fold(const ChunkIssue& c, uint32_t acc_first, uint32_t& woff) {
+  constexpr uint32_t RP = 2u * W;
+  constexpr uint32_t LAY = W == 64 ? 2u : (W == 32 ? 4u : 6u);
+  constexpr uint32_t D_HI = ((8u * RP) >> 4) | (1u << 14) | (LAY << 29);
+  const uint32_t a_hi_lo = ((c.sa & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t a_lo_lo = (((c.sa + c.a_tile) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const uint32_t sb = c.smem_base + woff;
+    woff += align1k(3u * c.ntile4 * (uint32_t)W);
+    const uint32_t b_lo = ((sb & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+    for (int ka = 0; ka < NK; ++ka) {
+      const uint32_t shift = (uint32_t)(dy * (int)RP + 2 * ka);     // 16 box pixels per filter row, immediate
+      umma_bf16_w(c.d, a_hi_lo + shift, D_HI, b_lo + 2 * ka, D_HI, c.idesc2, (dy == 0 && ka == 0) ? acc_first : 1u, c.el);
+      umma_bf16_w(c.d, a_lo_lo + shift, D_HI, b_lo + 2 * ka, D_HI, c.idesc1, 1u, c.el);
+    }
+  }
+}
+
+__device__ __forceinline__ void issue_dispatch_fold(uint32_t code, const ChunkIssue& ci, uint32_t accf, uint32_t& woff) {
+  switch (code & 0xFFFu) {
+    case 64u | (4u << 8): issue_chunk_fold<64, 4>(ci, accf, woff); break;
+    case 64u | (3u << 8): issue_chunk_fold<64, 3>(ci, accf, woff); break;
+    case 64u | (2u << 8): issue_chunk_fold<64, 2>(ci, accf, woff); break;
+    case 64u | (1u << 8): issue_chunk_fold<64, 1>(ci, accf, woff); break;
+    case 32u | (2u << 8): issue_chunk_fold<32, 2>(ci, accf, woff); break;
+    case 32u | (1u << 8): issue_chunk_fold<32, 1>(ci, accf, woff); break;
+    default: issue_chunk_fold<16, 1>(ci, accf, woff); break;
+  }
+}
+
 struct MmaCtx {
   uint32_t el, tmem_d, smem_base, a_base, a_tile, b_base, b_tile, bar0, idesc1, idesc2;
   int total_tiles;
@@ -132,7 +172,7 @@ struct MmaCtx {
 __device__ __forceinline__ void turn_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void turn_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-template <int KS, bool RES>
+template <int KS, bool RES, bool FOLD = false>
 __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& m, const int role) {
   const uint32_t el = m.el;
   const int SA = L.stages_a, nchunk = L.nchunk, ntile = L.ntile;
@@ -156,7 +196,7 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
       if (dbg) wait_tmem += clock64() - w0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    ci.d = m.tmem_d + (uint32_t)(acc * 2 * ntile);
+    ci.d = m.tmem_d + (uint32_t)(acc * (FOLD ? 6 : 2) * ntile);
     uint32_t woff = 0;
     for (int j = 0; j < nchunk; ++j, ++ia) {
       const uint32_t code = L.chunk[j];
@@ -169,7 +209,8 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
         ci.sa = m.a_base + st * 2 * m.a_tile;
         if (ia > 0) turn_wait(1 + role);
         if (dbg && el && ia < 48) L.dbg_ts[40 + (ia >> 1)] = clock64();
-        issue_dispatch<KS, RES>(code, ci, j == 0 ? 0u : 1u, woff, ib);
+        if (FOLD) issue_dispatch_fold(code, ci, j == 0 ? 0u : 1u, woff);
+        else issue_dispatch<KS, RES>(code, ci, j == 0 ? 0u : 1u, woff, ib);
         if (ia < last_ia) turn_pass(2 - role);
         if (dbg && el && ia < 48) L.dbg_ts[64 + (ia >> 1)] = clock64();
         umma_commit_p(empty_a0 + 8u * st, el);
@@ -178,7 +219,8 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
       } else {
         // the other warp's chunk: keep the weight cursor / ring counters in step
         const uint32_t w = code & 0xFFu;
-        if (RES) woff += (uint32_t)(KS * KS) * align1k(ci.ntile4 * w);
+        if (FOLD) woff += 3u * align1k(3u * ci.ntile4 * w);
+        else if (RES) woff += (uint32_t)(KS * KS) * align1k(ci.ntile4 * w);
         else ib += KS * KS;
       }
       if (++st == SA) { st = 0; ph_a ^= 1u; }
@@ -253,7 +295,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
           const int cpad = L.seg_cpad[s], w = L.seg_w[s];
           const CUtensorMap* wm = maps + L.w_map[w >> 5];          // 16 -> 0, 32 -> 1, 64 -> 2
           const uint32_t bt = (uint32_t)ntile * 2u * w;            // hi rows, lo rows directly behind them
-          for (int c0 = 0; c0 < cpad; c0 += w)
+          for (int c0 = 0; c0 < cpad; c0 += w) {
+            if (L.fold) {
+              // per filter row one B tile: [hi(dx=0); hi(1); hi(2); lo(0); lo(1); lo(2)], ntile rows each
+              for (int dy = 0; dy < 3; ++dy) {
+                for (int half = 0; half < 2; ++half)
+                  for (int dx = 0; dx < 3; ++dx)
+                    tma_load_2d_p(smem_base + off + (uint32_t)(half * 3 + dx) * bt, wm + half, wbar,
+                                  L.seg_koff[s] + (dy * 3 + dx) * cpad + c0, n0, el);
+                off += align1k(6 * bt);
+              }
+              continue;
+            }
             for (int tap = 0; tap < NT; ++tap) {
               if (!((L.tap_mask >> tap) & 1)) continue;
               const int koff = L.seg_koff[s] + tap * cpad + c0;
@@ -261,6 +314,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
               tma_load_2d_p(smem_base + off + bt, wm + 1, wbar, koff, n0, el);
               off += align1k(2 * bt);
             }
+          }
         }
       }
       // ... and do not read the previous layer's activations before it has completed and flushed.
@@ -273,7 +327,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
         const int img = t / tiles_per_img;
         const int r = t - img * tiles_per_img;
         const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
-        const int y0 = ty * 16, x0 = tx * 8;
+        const int y0 = L.fold ? ty * 8 : ty * 16, x0 = L.fold ? tx * 14 : tx * 8;
         for (int j = 0; j < nchunk; ++j, ++ia) {
           const uint32_t code = L.chunk[j];
           const int w = (int)(code & 0xFFu), s = (int)((code >> 12) & 0xFu), c0 = (int)(code >> 16);
@@ -325,8 +379,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
       // the epilogue adds the two column halves.  A (4 KB per MMA) is the shared-memory-bandwidth
       // bound of small-N layers, so reading A_hi once instead of twice is a 1.5x saving.
       const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
-      const uint32_t idesc1 = idesc_base | ((uint32_t)(ntile >> 3) << 17);
-      const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * ntile) >> 3) << 17);
+      const uint32_t idesc1 = idesc_base | ((uint32_t)(((L.fold ? 3 : 1) * ntile) >> 3) << 17);
+      const uint32_t idesc2 = idesc_base | ((uint32_t)(((L.fold ? 6 : 2) * ntile) >> 3) << 17);
       if (L.resident) mbar_wait(wbar, 0);
       if (dbg && el && role == 0) L.dbg_ts[2] = clock64();
       MmaCtx mc;
@@ -334,7 +388,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
       mc.b_base = b_base; mc.b_tile = b_tile; mc.bar0 = bar0; mc.total_tiles = total_tiles; mc.dbg = dbg;
       mc.idesc1 = idesc1; mc.idesc2 = idesc2;
       const int ks = NT == 1 ? 1 : (L.tap_mask == 0x1FF ? 3 : 2);
-      if (L.resident) {
+      if (L.fold) {
+        mma_warp_loop<3, true, true>(L, mc, role);
+      } else if (L.resident) {
         if (ks == 3) mma_warp_loop<3, true>(L, mc, role);
         else if (ks == 1) mma_warp_loop<1, true>(L, mc, role);
         else mma_warp_loop<2, true>(L, mc, role);
@@ -361,8 +417,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
       const int img = t / tiles_per_img;
       const int r = t - img * tiles_per_img;
       const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
-      const int oy = ty * 16 + (m >> 3), ox = tx * 8 + (m & 7);
-      const bool inside = (oy < L.Hout) && (ox < L.Wout);
+      // fold: accumulator row m = input column x' = m & 15 of row m >> 4; output column = x' - 1 + tile origin
+      const int oy = L.fold ? ty * 8 + (m >> 4) : ty * 16 + (m >> 3);
+      const int ox = L.fold ? tx * 14 + (m & 15) - 1 : tx * 8 + (m & 7);
+      const bool inside = (oy < L.Hout) && (ox < L.Wout) && (!L.fold || ((m & 15) >= 1 && (m & 15) <= 14));
       if (dbg) w0 = clock64();
       mbar_wait(tmem_full(acc), (tc_ >> 1) & 1);
       if (dbg) wait_epi += clock64() - w0;
@@ -384,7 +442,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
         a00 = ab + ((size_t)ay0 * L.add_W + ax0) * L.add_cs; a01 = ab + ((size_t)ay0 * L.add_W + ax1) * L.add_cs;
         a10 = ab + ((size_t)ay1 * L.add_W + ax0) * L.add_cs; a11 = ab + ((size_t)ay1 * L.add_W + ax1) * L.add_cs;
       }
-      const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * ntile);
+      const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (L.fold ? 6 : 2) * ntile);
       // the accumulator buffer goes back to the MMA warps as soon as it has been READ (not after the stores):
       // with only two buffers the MMAs of tile i+2 otherwise wait for the whole epilogue of tile i
       auto release = [&]() {
@@ -429,7 +487,37 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
         oh[0] = h[0]; oh[1] = h[1];
         ol[0] = l[0]; ol[1] = l[1];
       };
-      if (ntile <= 32) {
+      if (L.fold) {
+        // six 16-column pieces per 16 output channels: (hi, lo) parts of the dx = 0, 1, 2 blocks.  Output column x takes
+        // block 0 from input column x - 1 (one lane down), block 1 from x, block 2 from x + 1 (one lane up); the 16
+        // lanes of an accumulator row are one row of the tile, and lanes 0 / 15 of a row store nothing.
+        const int ng = (ntile == 32 && n0 + 16 < L.cout_store) ? 2 : 1;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g >= ng) break;
+          uint32_t h0[16], h1[16], h2[16], l0[16], l1[16], l2[16];
+          const uint32_t c = trow + (uint32_t)(g * 16);
+          tmem_ld16_nowait(c, h0);
+          tmem_ld16_nowait(c + (uint32_t)ntile, h1);
+          tmem_ld16_nowait(c + (uint32_t)(2 * ntile), h2);
+          tmem_ld16_nowait(c + (uint32_t)(3 * ntile), l0);
+          tmem_ld16_nowait(c + (uint32_t)(4 * ntile), l1);
+          tmem_ld16_nowait(c + (uint32_t)(5 * ntile), l2);
+          tmem_ld_wait16(h0); tmem_ld_wait16(h1); tmem_ld_wait16(h2);
+          tmem_ld_wait16(l0); tmem_ld_wait16(l1); tmem_ld_wait16(l2);
+          if (g == ng - 1) release();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = __uint_as_float(h0[i]) + __uint_as_float(l0[i]);
+            const float e1 = __uint_as_float(h1[i]) + __uint_as_float(l1[i]);
+            const float e2 = __uint_as_float(h2[i]) + __uint_as_float(l2[i]);
+            const float left = __shfl_up_sync(0xffffffffu, e0, 1), right = __shfl_down_sync(0xffffffffu, e2, 1);
+            v[i] = ((left + e1) + right) + bias_r[g][i];
+          }
+          finish16(v, n0 + g * 16);
+        }
+      } else if (ntile <= 32) {
         // whole accumulator row in registers (2 or 4 loads in flight), buffer released, then the math and the stores
         uint32_t r0[16], r1[16], r2[16], r3[16];
         const bool two = ntile == 32 && n0 + 16 < L.cout_store;
@@ -549,10 +637,11 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
     const int w = L->seg_w[s];
     if (w > wmax) wmax = w;
     const int nchunks = (L->seg_cpad[s] + w - 1) / w;
-    const size_t bt = align_up((size_t)2 * L->ntile * 2 * w, 1024);   // [hi rows ; lo rows] of one tap
-    const int nact = __builtin_popcount((unsigned)L->tap_mask & ((1u << L->taps) - 1u));
+    size_t bt = align_up((size_t)2 * L->ntile * 2 * w, 1024);   // [hi rows ; lo rows] of one tap
+    int nact = __builtin_popcount((unsigned)L->tap_mask & ((1u << L->taps) - 1u));
+    if (L->fold) { bt = align_up((size_t)6 * L->ntile * 2 * w, 1024); nact = 3; }   // one tile per filter row
     w_total += (size_t)nchunks * nact * bt;
-    w_tx += (size_t)nchunks * nact * 2 * (size_t)L->ntile * 2 * w;
+    w_tx += (size_t)nchunks * (L->fold ? 9 : nact) * 2 * (size_t)L->ntile * 2 * w;
   }
   const size_t a_tile = align_up((size_t)L->hx * L->hy * 2 * wmax, 1024);
   const size_t b_tile = align_up((size_t)2 * L->ntile * 2 * wmax, 1024);
@@ -571,6 +660,7 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
     *smem_bytes = w_total + (size_t)L->stages_a * 2 * a_tile + 1024;
     return true;
   }
+  if (L->fold) return false;          // the folded form needs resident weights: the caller retries unfolded
   L->resident = 0;
   L->w_bytes_total = 0;
   L->w_tx_total = 0;

@@ -52,6 +52,13 @@ def test_every_conv_layer_tcgen05(pf_lib, bg_shapes, monkeypatch):
     print("worst per-layer relative error (tcgen05 split-bf16):", worst)
 
 
+def test_every_conv_layer_tcgen05_unfolded(pf_lib, bg_shapes, monkeypatch):
+    """The 3x3 layers on the one-MMA-pair-per-tap form of the halo kernel (the dx-folded form is the default)."""
+    monkeypatch.delenv("PF_TC_FORCE_SIMT", raising=False)
+    monkeypatch.setenv("PF_HALO_NO_FOLD", "1")
+    layer_sweep(pf_lib, bg_shapes, 1e-4)
+
+
 @pytest.mark.parametrize("shape,final", [((1, 3, 64, 128), None), ((2, 3, 128, 192), (256, 384)), ((1, 3, 256, 512), None)])
 def test_whole_net_tcgen05(pf_lib, bg_shapes, shape, final):
     b, t, h, w = shape
