@@ -1028,12 +1028,28 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   const char* ff = getenv("PF_HALO_FOLD_MIN_K");
   const int fold_min_k = ff && ff[0] ? atoi(ff) : 48;
   L->fold = (!no_fold && c.ksize == 3 && L->tap_mask == 0x1FF && ntile <= 32 && kin >= fold_min_k) ? 1 : 0;
-  if (L->fold) { L->hx = 16; L->hy = 10; }
-  if (!halo_plan_smem(L, smem)) {
-    if (!L->fold) return 1;
-    L->fold = 0; L->hx = 10; L->hy = 18;
-    if (!halo_plan_smem(L, smem)) return 1;
+  if (L->fold) {
+    // The folded form needs resident weights and a ring of >= 3 activation stages.  A 32-cout layer whose weights
+    // leave no room for that (K >~ 100) is split along N instead: two CTAs per tile with 16 couts each (half the
+    // weights per SM; the activation boxes are fetched twice, from L2).
+    const char* fs = getenv("PF_HALO_FOLD_SPLIT");
+    const int split_mode = fs && fs[0] ? atoi(fs) : 1;       // 0 never, 1 when n = 32 does not fit, 2 always
+    L->hx = 16; L->hy = 10;
+    bool planned = halo_plan_smem(L, smem);                  // false when the weights cannot be resident
+    const bool roomy = planned && L->stages_a >= 3;
+    // measured (batch 8): 135->28 at 1/8 (weights not resident at n = 32) 115 -> 77 us, 96->18 / 114->30 at 1/16
+    // (resident with 2 stages, 4 tiles per SM) 31 -> 22 / 37 -> 27 us, but 91->28 at 1/4 (resident with 2 stages,
+    // 63 tiles per SM) 196 -> 248 us: fetching every activation box twice costs more than the shallow ring there.
+    const bool few_tiles = cdiv(io.Wout, 14) * cdiv(io.Hout, 8) * io.b < 16 * kNumSMs;
+    if (ntile == 32 && c.coutpad == 32 && split_mode && (!planned || (!roomy && few_tiles) || split_mode == 2)) {
+      HaloLayer T = *L;
+      size_t sm2 = 0;
+      T.ntile = 16;
+      if (halo_plan_smem(&T, &sm2) && T.stages_a >= 3) { *L = T; *smem = sm2; ntile = 16; nb = 2; planned = true; }
+    }
+    if (!planned) { L->fold = 0; L->hx = 10; L->hy = 18; }     // (resident with 2 stages still beats the unfolded form)
   }
+  if (!L->fold && !halo_plan_smem(L, smem)) return 1;
   for (int s = seg0; s < seg1; ++s) {
     const int k = s - seg0;
     L->seg_map[k] = (int)maps->size();
