@@ -988,6 +988,22 @@ static int build_tc_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUte
   return 0;
 }
 
+// Shared-memory plan of the dx-folded form; false when the weights cannot be resident.  A plan left with a 2-deep
+// ring of 40 KB stages stages 32-channel chunks instead (twice the boxes, half the stage size) when that gives >= 3.
+static bool plan_fold(HaloLayer* T, size_t* smem) {
+  T->fold = 1; T->hx = 16; T->hy = 10;
+  if (!halo_plan_smem(T, smem)) return false;
+  if (T->stages_a < 3) {
+    HaloLayer V = *T;
+    size_t sm2 = 0;
+    bool any = false;
+    for (int k = 0; k < V.nseg; ++k)
+      if (V.seg_w[k] == 64) { V.seg_w[k] = 32; any = true; }
+    if (any && halo_plan_smem(&V, &sm2) && V.stages_a >= 3) { *T = V; *smem = sm2; }
+  }
+  return true;
+}
+
 // Halo-kernel plan of a 3x3 / stride-1 conv.  Returns 1 when the layer does not fit (caller falls
 // back to the per-tap kernel), 0 on success, <0 / cudaError on failure.
 static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUtensorMap>* maps, HaloLayer* L,
@@ -1034,22 +1050,39 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     // weights per SM; the activation boxes are fetched twice, from L2).
     const char* fs = getenv("PF_HALO_FOLD_SPLIT");
     const int split_mode = fs && fs[0] ? atoi(fs) : 1;       // 0 never, 1 when n = 32 does not fit, 2 always
-    L->hx = 16; L->hy = 10;
-    bool planned = halo_plan_smem(L, smem);                  // false when the weights cannot be resident
+    bool planned = plan_fold(L, smem);                       // false when the weights cannot be resident
     const bool roomy = planned && L->stages_a >= 3;
     // measured (batch 8): 135->28 at 1/8 (weights not resident at n = 32) 115 -> 77 us, 96->18 / 114->30 at 1/16
     // (resident with 2 stages, 4 tiles per SM) 31 -> 22 / 37 -> 27 us, but 91->28 at 1/4 (resident with 2 stages,
-    // 63 tiles per SM) 196 -> 248 us: fetching every activation box twice costs more than the shallow ring there.
+    // 63 tiles per SM) 196 -> 248 us: fetching every activation box twice costs more than the shallow ring there
+    // (32-channel chunks, plan_fold, give it 4 stages instead: 196 -> 153 us).
     const bool few_tiles = cdiv(io.Wout, 14) * cdiv(io.Hout, 8) * io.b < 16 * kNumSMs;
     if (ntile == 32 && c.coutpad == 32 && split_mode && (!planned || (!roomy && few_tiles) || split_mode == 2)) {
       HaloLayer T = *L;
       size_t sm2 = 0;
       T.ntile = 16;
-      if (halo_plan_smem(&T, &sm2) && T.stages_a >= 3) { *L = T; *smem = sm2; ntile = 16; nb = 2; planned = true; }
+      if (plan_fold(&T, &sm2) && T.stages_a >= 3) { *L = T; *smem = sm2; ntile = 16; nb = 2; planned = true; }
     }
-    if (!planned) { L->fold = 0; L->hx = 10; L->hy = 18; }     // (resident with 2 stages still beats the unfolded form)
+    if (!planned) {                                          // (resident with 2 stages still beats the unfolded form)
+      L->fold = 0; L->hx = 10; L->hy = 18;
+      for (int k = 0; k < L->nseg; ++k) L->seg_w[k] = halo_chunk_width(L->seg_cpad[k]);
+    }
   }
   if (!L->fold && !halo_plan_smem(L, smem)) return 1;
+  if (!L->fold && !no_fold && c.ksize == 3 && L->tap_mask == 0x1FF && ntile == 48 && c.coutpad == 48 && kin >= fold_min_k &&
+      !L->resident) {
+    // 48 couts whose weights have to be streamed per tile: three folded CTAs of 16 couts with resident weights instead
+    // (108->46 at 1/8: 114 -> 102 us)
+    const char* f48 = getenv("PF_HALO_FOLD_48");
+    if (!(f48 && f48[0] == '0')) {
+      HaloLayer T = *L;
+      size_t sm2 = 0;
+      T.ntile = 16;
+      if (plan_fold(&T, &sm2) && T.stages_a >= 3) { *L = T; *smem = sm2; ntile = 16; nb = 3; }
+    }
+  }
+  used[0] = used[1] = used[2] = false;
+  for (int k = 0; k < L->nseg; ++k) used[L->seg_w[k] >> 5] = true;
   for (int s = seg0; s < seg1; ++s) {
     const int k = s - seg0;
     L->seg_map[k] = (int)maps->size();
