@@ -262,8 +262,13 @@ def main():
     fps = world * B * K / (ms_total_max / 1e3)
     warp_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in ev_a)
     net_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in ev_b)
-    if os.environ.get('PF_BENCH_DEBUG'):
-        print('warp ms per step:', ['%.2f' % a.elapsed_time(b_) for a, b_ in ev_a], file=sys.stderr)
+    step_a = [a.elapsed_time(b_) for a, b_ in ev_a]
+    step_b = [a.elapsed_time(b_) for a, b_ in ev_b]
+    gaps = [ev_b[i][1].elapsed_time(ev_a[i + 1][0]) for i in range(K - 1)]
+    if os.environ.get('PF_BENCH_DEBUG') or max(step_a) > 2 * statistics.median(step_a) or max(step_b) > 2 * statistics.median(step_b):
+        print('stage A ms per step:', ['%.2f' % x for x in step_a], file=sys.stderr)
+        print('stage B ms per step:', ['%.2f' % x for x in step_b], file=sys.stderr)
+        print('gap ms between steps:', ['%.2f' % x for x in gaps], file=sys.stderr)
 
     # per-kernel split of Stage B (separate pass, events between all kernels; not part of `value`)
     Kp = min(K, 5)

@@ -87,6 +87,7 @@ struct pf_bgnet {
     std::vector<TcLayer> layers;             // indexed by conv (per-tap kernel: 1x1 convs, fallbacks)
     std::vector<HaloLayer> halos;            // indexed by conv (halo kernel: 3x3 stride-1 and 1x1 convs)
     std::vector<HaloLayer> halos_low;        // indexed by conv: low-resolution half of a fused conv1x1_up
+    std::vector<char> pool_fused;            // indexed by step: the pool runs in the producing conv's epilogue
     std::vector<int> nblocks_low;
     std::vector<size_t> smem_low;
     std::vector<int> nblocks;
@@ -226,6 +227,7 @@ static void build_topology(pf_bgnet* net) {
       Step st; st.type = STEP_POOL; st.in = {pout};
       net->steps.push_back(st);
       pending_pool_step = (int)net->steps.size() - 1;
+      net->convs[ci].pool_step = pending_pool_step;
       idx++;
     } else {
       cur_segs = {pout};
@@ -1143,6 +1145,7 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
   }
   P.smem.assign(nc, 0);
   P.use_tc.assign(nc, 0);
+  P.pool_fused.assign(net->steps.size(), 0);
   for (size_t i = 0; i < nc; ++i) {
     const ConvDesc& c = net->convs[i];
     if ((int)i == net->first_conv || c.exec_stride() != 1) continue;
@@ -1187,7 +1190,22 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
     }
     const bool need_halo = c.s2d_in || c.s2d_out;
     int rc = (net->no_halo && !need_halo) ? 1 : build_halo_layer(net, (int)i, io, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i]);
-    if (rc == 0) { P.use_tc[i] = 2; continue; }
+    if (rc == 0) {
+      P.use_tc[i] = 2;
+      // AvgPool2d(2,2) behind a 1x1 transition conv: averaged in the conv's epilogue (warp shuffles over the 16 x 8
+      // tile), so the full-resolution tensor is never written (base.5 + pool at 1/4 resolution: 162 + 57 us per 8 frames)
+      const char* np_ = getenv("PF_TC_NO_FUSE_POOL");
+      if (c.pool_step >= 0 && !(np_ && np_[0] == '1') && !P.halos[i].fold && !P.halos[i].s2d_block) {
+        const SegRef& po = net->steps[c.pool_step].out;
+        HaloLayer& hl = P.halos[i];
+        hl.pool = 1;
+        hl.out_hi = reinterpret_cast<__nv_bfloat16*>(a.ptr(po.buf, po.coff));
+        hl.out_lo = reinterpret_cast<__nv_bfloat16*>(a.ptr_lo(po.buf, po.coff));
+        hl.out_cs = net->bufs[po.buf].cstride; hl.out_img_stride = a.img_elems[po.buf];
+        P.pool_fused[c.pool_step] = 1;
+      }
+      continue;
+    }
     if (rc != 1) return rc;
     rc = build_tc_layer(net, (int)i, io, &maps, &P.layers[i], &P.nblocks[i], &P.smem[i]);
     if (rc) return rc;
@@ -1370,7 +1388,10 @@ extern "C" size_t pf_bgnet_workspace_bytes(const pf_bgnet_t* net, int b, int H, 
 extern "C" int pf_bgnet_launches_per_forward(const pf_bgnet_t* net) {
   if (!net) return PF_EINVAL;
   int n = 0;
-  for (auto& s : net->steps) {
+  for (size_t k = 0; k < net->steps.size(); ++k) {
+    const Step& s = net->steps[k];
+    if (s.type == STEP_POOL && net->precision == 1 && !net->force_simt && k < net->plan.pool_fused.size() && net->plan.pool_fused[k])
+      continue;                                            // averaged in the producing conv's epilogue
     n += (s.type == STEP_HEAD) ? 2 : 1;
     if (s.type == STEP_CONV && net->convs[s.conv].up_nseg > 0) n += 1;
   }
@@ -1472,6 +1493,8 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         break;
       }
       case STEP_POOL: {
+        const int k = step_i - 1;
+        if (net->precision == 1 && !net->force_simt && k < (int)net->plan.pool_fused.size() && net->plan.pool_fused[k]) break;
         const SegRef& in = s.in[0];
         const BufDesc& ib = net->bufs[in.buf];
         const BufDesc& ob = net->bufs[s.out.buf];

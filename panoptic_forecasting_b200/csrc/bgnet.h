@@ -46,6 +46,7 @@ struct ConvDesc {
   // interpolation in the epilogue: relu(W_skip * skip + up(W_up * x) + b).  No upsampled tensor is materialised.
   int up_nseg = 0;
   int ybuf = -1;
+  int pool_step = -1;       // index of the AvgPool2d(2,2) step that consumes this conv's output (hardnet.py:293-294)
   int exec_stride() const { return s2d_in ? 1 : stride; }
   std::vector<float> w_host;     // folded, packed like w_dev (kept for re-packing by the tensor-core path)
   std::vector<float> bias_host;

@@ -426,10 +426,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
       if (dbg) wait_epi += clock64() - w0;
       if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // pool: the even/even pixel of each 2x2 block stores the average, into the half-resolution tensor
+      const bool store_px = L.pool ? (((m & 9) == 0) && (oy >> 1) < (L.Hout >> 1) && (ox >> 1) < (L.Wout >> 1)) : inside;
       const size_t pix = L.s2d_block
                              ? (size_t)img * L.out_img_stride + ((size_t)(oy >> 1) * (L.Wout >> 1) + (ox >> 1)) * L.out_cs +
                                    (size_t)((oy & 1) * 2 + (ox & 1)) * L.s2d_block
-                             : (size_t)img * L.out_img_stride + ((size_t)oy * L.Wout + ox) * L.out_cs;
+                             : L.pool ? (size_t)img * L.out_img_stride + ((size_t)(oy >> 1) * (L.Wout >> 1) + (ox >> 1)) * L.out_cs
+                                      : (size_t)img * L.out_img_stride + ((size_t)oy * L.Wout + ox) * L.out_cs;
       // bilinear source of the optional additive term (conv1x1_up fused with TransitionUp)
       const float *a00 = nullptr, *a01 = nullptr, *a10 = nullptr, *a11 = nullptr;
       float aly = 0.f, alx = 0.f;
@@ -467,7 +470,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (!inside || (L.dbg_mode & 2)) return;
+        if (L.pool) {
+          // AvgPool2d(2,2) of the ReLU'd outputs: lane bits 0 / 3 are the column / row parity inside the 16 x 8 tile
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            v[i] = t * 0.25f;
+          }
+        }
+        if (!store_px || (L.dbg_mode & 2)) return;
         if (L.out_f32) {
           float4* o = reinterpret_cast<float4*>(L.out_f32 + pix + n);
 #pragma unroll

@@ -14,7 +14,7 @@ from test_bgnet_gpu import check_against, gpu_model
 pytestmark = pytest.mark.gpu
 
 
-def layer_sweep(pf_lib, bg_shapes, tol):
+def layer_sweep(pf_lib, bg_shapes, tol, hw=(24, 40)):
     sd = synthetic.make_bg_state_dict(bg_shapes, seed=2)
     m = gpu_model(sd, precision="tc")
     m._upload(torch.device("cuda", torch.cuda.current_device()))
@@ -25,7 +25,7 @@ def layer_sweep(pf_lib, bg_shapes, tol):
     for i in range(1, n + 1):
         assert pf_lib.pf_bgnet_conv_info(m._net, i, C.byref(info)) == 0
         name = info.name.decode()
-        H, W = (24, 40) if info.stride == 1 else (24, 48)
+        H, W = hw if info.stride == 1 else (hw[0], hw[1] + 8)
         x = torch.randn(2, info.cin, H, W, generator=g).relu()
         if i < n:
             ref = bg_oracle.conv_layer(sd, name, x, info.ksize, info.stride)
@@ -50,6 +50,13 @@ def test_every_conv_layer_tcgen05(pf_lib, bg_shapes, monkeypatch):
     monkeypatch.delenv("PF_TC_FORCE_SIMT", raising=False)
     worst = layer_sweep(pf_lib, bg_shapes, 1e-4)
     print("worst per-layer relative error (tcgen05 split-bf16):", worst)
+
+
+def test_every_conv_layer_tcgen05_many_tiles(pf_lib, bg_shapes, monkeypatch):
+    """Enough pixel tiles (> 148) that layers keep their full N per CTA: the n = 32 folded form, its 32-channel-chunk
+    and N-split fallbacks, 48..128-cout unfolded layers with resident / streamed weights.  Odd sizes: ragged 8x14 tiles."""
+    monkeypatch.delenv("PF_TC_FORCE_SIMT", raising=False)
+    layer_sweep(pf_lib, bg_shapes, 1e-4, hw=(100, 170))
 
 
 def test_every_conv_layer_tcgen05_unfolded(pf_lib, bg_shapes, monkeypatch):
