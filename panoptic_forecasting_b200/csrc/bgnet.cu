@@ -88,6 +88,7 @@ struct pf_bgnet {
     std::vector<HaloLayer> halos;            // indexed by conv (halo kernel: 3x3 stride-1 and 1x1 convs)
     std::vector<HaloLayer> halos_low;        // indexed by conv: low-resolution half of a fused conv1x1_up
     std::vector<char> pool_fused;            // indexed by step: the pool runs in the producing conv's epilogue
+    int head_amax = 0;                       // the head conv parks each quarter-resolution pixel's argmax in channel 15
     std::vector<int> nblocks_low;
     std::vector<size_t> smem_low;
     std::vector<int> nblocks;
@@ -641,7 +642,11 @@ __global__ void upsample_argmax_kernel(const float* __restrict__ q, int b, int n
 // Strip variant for the usual x4 case (3*sw < 1, fw % 4 == 0): one thread = 4 consecutive output
 // pixels of a row; they touch at most 3 source columns x 2 rows, loaded once (18 instead of 48 LDG.128).
 // Same interpolation arithmetic as upsample_argmax_kernel (bit-identical logits).
-template <bool FULL>
+// AMAX: channel 15 of every source pixel holds its own argmax (written by the head conv's epilogue).  If the six
+// source pixels a strip touches agree on class c, then c maximises every convex combination of them (first-maximum
+// ties included), so the strip is c without any interpolation; label maps are piecewise constant, so that is the
+// common case and the kernel becomes a byte-map expansion.  Strips on a class boundary take the full path.
+template <bool FULL, bool AMAX>
 __global__ void __launch_bounds__(256) upsample_argmax_strip_kernel(const float* __restrict__ q, int ncls, int h, int w, int fh, int fw,
                                                                     float sh, float sw, uint8_t* __restrict__ seg8,
                                                                     long long* __restrict__ seg64, float* __restrict__ full) {
@@ -662,6 +667,24 @@ __global__ void __launch_bounds__(256) upsample_argmax_strip_kernel(const float*
   const float4* p1[3] = {reinterpret_cast<const float4*>(base + (size_t)(y1 * w + cA) * 16),
                          reinterpret_cast<const float4*>(base + (size_t)(y1 * w + cB) * 16),
                          reinterpret_cast<const float4*>(base + (size_t)(y1 * w + cC) * 16)};
+  if (AMAX && !FULL) {
+    const int c00 = __float_as_int(__ldg(reinterpret_cast<const float*>(p0[0]) + 15));
+    const int c01 = __float_as_int(__ldg(reinterpret_cast<const float*>(p0[1]) + 15));
+    const int c02 = __float_as_int(__ldg(reinterpret_cast<const float*>(p0[2]) + 15));
+    const int c10 = __float_as_int(__ldg(reinterpret_cast<const float*>(p1[0]) + 15));
+    const int c11 = __float_as_int(__ldg(reinterpret_cast<const float*>(p1[1]) + 15));
+    const int c12 = __float_as_int(__ldg(reinterpret_cast<const float*>(p1[2]) + 15));
+    if (c00 == c01 && c00 == c02 && c00 == c10 && c00 == c11 && c00 == c12) {
+      const size_t o = ((size_t)img * fh + y) * fw + xs;
+      if (seg8) *reinterpret_cast<uchar4*>(seg8 + o) = make_uchar4((uint8_t)c00, (uint8_t)c00, (uint8_t)c00, (uint8_t)c00);
+      if (seg64) {
+        longlong2* o64 = reinterpret_cast<longlong2*>(seg64 + o);
+        o64[0] = make_longlong2(c00, c00);
+        o64[1] = make_longlong2(c00, c00);
+      }
+      return;
+    }
+  }
   float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   int arg[4] = {0, 0, 0, 0};
   bool a1[4], b1[4], b2[4];
@@ -1146,6 +1169,7 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
   P.smem.assign(nc, 0);
   P.use_tc.assign(nc, 0);
   P.pool_fused.assign(net->steps.size(), 0);
+  P.head_amax = 0;
   for (size_t i = 0; i < nc; ++i) {
     const ConvDesc& c = net->convs[i];
     if ((int)i == net->first_conv || c.exec_stride() != 1) continue;
@@ -1192,6 +1216,11 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
     int rc = (net->no_halo && !need_halo) ? 1 : build_halo_layer(net, (int)i, io, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i]);
     if (rc == 0) {
       P.use_tc[i] = 2;
+      if (head) {
+        const char* na = getenv("PF_TC_NO_AMAX");
+        P.head_amax = (net->num_classes <= 15 && !(na && na[0] == '1')) ? 1 : 0;
+        P.halos[i].amax_ncls = P.head_amax ? net->num_classes : 0;
+      }
       // AvgPool2d(2,2) behind a 1x1 transition conv: averaged in the conv's epilogue (warp shuffles over the 16 x 8
       // tile), so the full-resolution tensor is never written (base.5 + pool at 1/4 resolution: 162 + 57 us per 8 frames)
       const char* np_ = getenv("PF_TC_NO_FUSE_POOL");
@@ -1547,12 +1576,16 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         const size_t total = (size_t)b * final_h * final_w;
         if (final_w % 4 == 0 && 3.f * sw < 0.999f && (((size_t)out_seg_u8_dev) & 3) == 0 && (((size_t)out_seg_i64_dev) & 15) == 0) {
           const dim3 grid(cdiv(final_w / 4, 256), final_h, b);
+          const bool amax = net->precision == 1 && !net->force_simt && net->plan.head_amax && net->plan.use_tc[net->final_conv] == 2;
           if (out_full_dev)
-            upsample_argmax_strip_kernel<true><<<grid, 256, 0, st>>>(q, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev,
-                                                                    (long long*)out_seg_i64_dev, out_full_dev);
+            upsample_argmax_strip_kernel<true, false><<<grid, 256, 0, st>>>(q, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev,
+                                                                           (long long*)out_seg_i64_dev, out_full_dev);
+          else if (amax)
+            upsample_argmax_strip_kernel<false, true><<<grid, 256, 0, st>>>(q, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev,
+                                                                           (long long*)out_seg_i64_dev, nullptr);
           else
-            upsample_argmax_strip_kernel<false><<<grid, 256, 0, st>>>(q, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev,
-                                                                     (long long*)out_seg_i64_dev, nullptr);
+            upsample_argmax_strip_kernel<false, false><<<grid, 256, 0, st>>>(q, net->num_classes, h, w, final_h, final_w, sh, sw, out_seg_u8_dev,
+                                                                            (long long*)out_seg_i64_dev, nullptr);
         }
         else
           upsample_argmax_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(

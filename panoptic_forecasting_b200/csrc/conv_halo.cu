@@ -481,6 +481,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
         }
         if (!store_px || (L.dbg_mode & 2)) return;
         if (L.out_f32) {
+          if (L.amax_ncls > 0 && n == 0) {
+            // first maximum of the class logits (torch.argmax tie rule), parked in the padding channel for the
+            // fused upsample + argmax kernel: a full-resolution pixel whose source pixels agree needs no interpolation
+            float best = v[0];
+            int arg = 0;
+#pragma unroll
+            for (int i = 1; i < 15; ++i)
+              if (i < L.amax_ncls && v[i] > best) { best = v[i]; arg = i; }
+            v[15] = __int_as_float(arg);
+          }
           float4* o = reinterpret_cast<float4*>(L.out_f32 + pix + n);
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);

@@ -47,6 +47,7 @@ struct HaloLayer {
   int ntile, tmem_cols, stages_a, stages_b;
   uint32_t a_tile_bytes, b_tile_bytes;
   int resident;             // weights stay in shared memory for the whole kernel
+  int amax_ncls;            // > 0 (fp32 head only): channel 15 of every stored pixel carries argmax over the first amax_ncls channels (int bits)
   int pool;                 // 2x2 average pool fused into the epilogue: out_* address the pooled tensor (Hout/2 x Wout/2)
   int fold;                 // 3x3, ntile <= 32, resident: the three taps of a filter row folded into N (10 x 16 box, 8 x 14 output tiles)
   uint32_t w_bytes_total, w_tx_total;

@@ -102,3 +102,24 @@ def test_fused_conv1x1_up_path(pf_lib, bg_shapes, monkeypatch):
     out = gpu_model(sd, None, precision="tc").predict({k: v.cuda() for k, v in inp.items()}, {})
     scale = ref["logits"].abs().max().item()
     assert (out["logits"].cpu() - ref["logits"]).abs().max().item() <= 3e-4 * scale
+
+
+def test_label_only_fast_path_matches_interpolated_argmax(pf_lib, bg_shapes, monkeypatch):
+    """return_logits=False: strips of the full-resolution map whose quarter-resolution source pixels agree on the class
+    skip the interpolation (the head conv parks each source pixel's argmax in the padding channel).  Must equal the
+    argmax of the interpolated logits (the return_logits=True path) and the hint-free kernel (PF_TC_NO_AMAX=1)."""
+    h, w = 256, 512
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=12)
+    pc = synthetic.make_pc_inputs(2, 3, h, w, "R", seed=12)
+    inp = {"seg": pc["seg"].long(), "depth": pc["depth"].clamp(0.1, 200), "depth_mask": pc["depth_mask"]}
+    q = bg_oracle.predict(sd, inp, (2 * h, 2 * w))["orig_size_logits"]
+    sd["model.finalConv.bias"] = sd["model.finalConv.bias"] - q.mean((0, 2, 3))       # class-balanced logits
+    cu = {k: v.cuda() for k, v in inp.items()}
+    full = gpu_model(sd, (2 * h, 2 * w), precision="tc", return_logits=True).predict(cu, {})
+    fast = gpu_model(sd, (2 * h, 2 * w), precision="tc", return_logits=False, seg_dtype="uint8").predict(cu, {})["seg"]
+    monkeypatch.setenv("PF_TC_NO_AMAX", "1")
+    slow = gpu_model(sd, (2 * h, 2 * w), precision="tc", return_logits=False, seg_dtype="uint8").predict(cu, {})["seg"]
+    assert len(torch.unique(fast)) >= 5                                               # a real multi-class map
+    assert torch.equal(slow.long(), full["seg"].long())
+    n_diff = int((fast.long() != full["seg"].long()).sum())
+    assert n_diff <= 1e-5 * fast.numel(), n_diff
