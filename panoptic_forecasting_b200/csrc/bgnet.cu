@@ -318,36 +318,48 @@ struct FirstParams {
   float mean, std;
 };
 
-// The input window of a CTA ((2*8+1) x (2*32+1) pixels x t frames of labels, depth, mask) is staged by
+// The input window of a tile ((2*8+1) x (2*32+1) pixels x t frames of labels, depth, mask) is staged by
 // TMA (3 boxes per frame, image borders zero-filled), then one in-place pass turns it into the two arrays
 // the taps read: the table row index of every pixel and its normalised masked depth.
-__global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParams p) {
+// PERSISTENT: a CTA loops over tiles (grid = a multiple of the SM count) with TWO staging buffers, so the boxes of
+// tile k+1 are in flight while tile k is converted and convolved, and the 25 KB of tables are loaded once per CTA
+// (the one-tile-per-CTA version issued only 24 % of its slots: every CTA sat through its own TMA latency).
+// T > 0: the number of input frames is a compile-time constant, the frame loop unrolls and every depth-plane weight is
+// an immediate constant-bank operand of its FFMA (with a runtime frame index each weight first went through a
+// uniform-register load, LDCU c[0x3][UR + imm]: 72 of them per frame in front of 144 FFMAs).  T = 0: runtime p.t.
+template <int T>
+__global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParams p_in) {
+  FirstParams p = p_in;
+  if (T > 0) p.t = T;
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[2];
   const int lut_floats = 9 * p.t * (p.ncls + 1) * 16;
   const int wd_floats = 9 * p.t * 16;
   const int sum_floats = p.t * (p.ncls + 1) * 16;
   const int tab_floats = lut_floats + wd_floats + 16 + sum_floats;
-  // dynamic smem: [depth/dn: t x 17 x 68 f32][labels: t x 17 x 80 u8][mask: t x 17 x 80 u8][tables]
+  // dynamic smem: 2 x { [depth/dn: t x 17 x 72 f32][labels: t x 17 x 96 u8][mask: t x 17 x 96 u8] } [tables]
   // TMA destinations must be 128-byte aligned: align the dynamic window by hand
   unsigned char* sm0 = smraw + ((128u - ((uint32_t)__cvta_generic_to_shared(smraw) & 127u)) & 127u);
-  float* dn = reinterpret_cast<float*>(sm0);
-  uint8_t* lab = reinterpret_cast<uint8_t*>(dn + p.t * F_DFRAME);
-  uint8_t* msk = lab + p.t * F_LFRAME;
-  float* lut = reinterpret_cast<float*>(msk + p.t * F_LFRAME);
+  const int stage_bytes = p.t * (F_DFRAME * 4 + 2 * F_LFRAME);
+  float* lut = reinterpret_cast<float*>(sm0 + 2 * stage_bytes);
   const float* lutsum = lut + lut_floats + wd_floats + 16;
   const int tid = threadIdx.x;
-  const int tiles_x = (p.Wo + F_TW - 1) / F_TW;
-  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
-  const int img = blockIdx.y;
-  const int oy0 = ty * F_TH, ox0 = tx * F_TW;
-  const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
-  if (tid == 0) {
-    tc::mbar_init(bar_a, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t bytes = (uint32_t)p.t * F_IH * (F_DPITCH * 4 * (p.use_depth ? 1 : 0) + F_LPITCH * (p.use_depth ? 2 : 1));
-    tc::mbar_expect_tx(bar_a, bytes);
+  const int tiles_x = (p.Wo + F_TW - 1) / F_TW, tiles_y = (p.Ho + F_TH - 1) / F_TH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int total_tiles = tiles_per_img * p.b;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+  const uint32_t stage_tx = (uint32_t)p.t * F_IH * (F_DPITCH * 4 * (p.use_depth ? 1 : 0) + F_LPITCH * (p.use_depth ? 2 : 1));
+  // thread 0: all boxes of tile `tile` into staging buffer `st`
+  auto issue = [&](int tile, int st) {
+    const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+    const int ty = r / tiles_x, tx = r - ty * tiles_x;
+    const int iy0 = ty * F_TH * 2 - 1, ix0 = tx * F_TW * 2 - 1;
+    unsigned char* base = sm0 + st * stage_bytes;
+    float* dn = reinterpret_cast<float*>(base);
+    uint8_t* lab = base + p.t * F_DFRAME * 4;
+    uint8_t* msk = lab + p.t * F_LFRAME;
+    const uint32_t bar_a = bar0 + 8u * st;
+    tc::mbar_expect_tx(bar_a, stage_tx);
     for (int f = 0; f < p.t; ++f) {
       const int z = img * p.t + f;
       // label / mask planes are fetched as 32-bit words starting 15 pixels left of the window
@@ -365,6 +377,12 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
                        "r"(xw), "r"(z * p.H + iy0) : "memory");
       }
     }
+  };
+  if (tid == 0) {
+    tc::mbar_init(bar0, 1);
+    tc::mbar_init(bar0 + 8u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((int)blockIdx.x < total_tiles) issue((int)blockIdx.x, 0);
   }
   // tables while the boxes are in flight
   {
@@ -372,45 +390,47 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
     float4* dst = reinterpret_cast<float4*>(lut);
     for (int i = tid; i < tab_floats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  __syncthreads();                 // barrier initialised / tables visible
-  tc::mbar_wait(bar_a, 0);
-  // in-place conversion: label -> table row (ncls = zero row for padding and ids >= num_classes),
-  // depth -> (d - mean) / std * mask (bg_model.py:50-51,67-68), 0 outside the image
-  // One warp per staged row (uniform frame / row / row-in-bounds), lanes over its 65 columns; the depth is
-  // normalised with a multiply by 1/std (Stage B is a float path: 1 ulp of the input is far inside its tolerance).
-  {
-    const int warp = tid >> 5, lane = tid & 31;
-    const float inv_std = __fdiv_rn(1.0f, p.std);
-    for (int row = warp; row < p.t * F_IH; row += (F_TH * F_TW) / 32) {
-      const int f = row / F_IH, hy = row - f * F_IH;
-      const int iy = iy0 + hy;
-      const bool rowin = iy >= 0 && iy < p.H;
-      uint8_t* lrow = lab + f * F_LFRAME + hy * F_LPITCH + F_LOFF;
-      const uint8_t* mrow = msk + f * F_LFRAME + hy * F_LPITCH + F_LOFF;
-      float* drow = dn + f * F_DFRAME + hy * F_DPITCH + F_DOFF;
-#pragma unroll
-      for (int hx = lane; hx < F_IW; hx += 32) {
-        const int ix = ix0 + hx;
-        const bool inb = rowin && ix >= 0 && ix < p.W;
-        const uint8_t lv = lrow[hx];
-        lrow[hx] = (inb && lv < p.ncls) ? lv : (uint8_t)p.ncls;
-        if (p.use_depth) {
-          float d = 0.f;
-          if (inb) {
-            const float v = __fmul_rn(__fadd_rn(drow[hx], -p.mean), inv_std);
-            d = mrow[hx] ? v : __fmul_rn(v, 0.0f);
-          }
-          drow[hx] = d;
-        }
-      }
-    }
+  __syncthreads();                 // barriers initialised / tables visible
+  int k = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
+  const int st = k & 1;
+  if (tid == 0 && tile + (int)gridDim.x < total_tiles) {
+    // the other buffer was last read (generic proxy) before the __syncthreads that ended the previous iteration
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    issue(tile + (int)gridDim.x, st ^ 1);
   }
-  __syncthreads();
+  const int img = tile / tiles_per_img, r_ = tile - img * tiles_per_img;
+  const int ty = r_ / tiles_x, tx = r_ - ty * tiles_x;
+  const int oy0 = ty * F_TH, ox0 = tx * F_TW;
+  const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+  unsigned char* sbase = sm0 + st * stage_bytes;
+  float* dn = reinterpret_cast<float*>(sbase);
+  uint8_t* lab = sbase + p.t * F_DFRAME * 4;
+  uint8_t* msk = lab + p.t * F_LFRAME;
+  tc::mbar_wait(bar0 + 8u * st, (uint32_t)((k >> 1) & 1));
+  // No conversion pass over the staged window (it was a third of the kernel's instructions, ncu source view): the taps
+  // clamp the label to the zero row (ids >= num_classes, bg_model.py:54-55) and normalise / mask the depth
+  // (bg_model.py:50-51,67-68) as they read.  Outside the image TMA filled zeros: mask 0 zeroes the depth term, but
+  // label 0 is a real class, so tiles on the image border first overwrite their out-of-image labels with the zero row.
+  if (iy0 < 0 || ix0 < 0 || iy0 + F_IH > p.H || ix0 + F_IW > p.W) {           // tile-uniform
+    for (int i = tid; i < p.t * F_IH * F_IW; i += blockDim.x) {
+      const int f = i / (F_IH * F_IW);
+      const int r = i - f * (F_IH * F_IW);
+      const int hy = r / F_IW, hx = r - hy * F_IW;
+      const int iy = iy0 + hy, ix = ix0 + hx;
+      if (!(iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)) lab[f * F_LFRAME + hy * F_LPITCH + hx + F_LOFF] = (uint8_t)p.ncls;
+    }
+    __syncthreads();
+  }
+  const float inv_std = __fdiv_rn(1.0f, p.std), neg_mean = -p.mean;
   const int py = tid / F_TW, px = tid % F_TW;
-  float acc[16];
+  // 16 output channels as 8 fp32 pairs: the table rows are added with sm_100's packed FADD2 (two IEEE fp32 adds per
+  // issue slot); this kernel is issue-bound (ncu: 472 M warp instructions per 16 frames, 61 % issue-active, no memory stall)
+  float2 acc[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = c_first_wd[9 * p.t * 16 + j];
-  for (int f = 0; f < p.t; ++f) {
+  for (int j = 0; j < 8; ++j) acc[j] = make_float2(c_first_wd[9 * p.t * 16 + 2 * j], c_first_wd[9 * p.t * 16 + 2 * j + 1]);
+#pragma unroll
+  for (int f = 0; f < (T > 0 ? T : p.t); ++f) {
     const int l0 = f * F_LFRAME + (py * 2) * F_LPITCH + px * 2 + F_LOFF;
     const int d0 = f * F_DFRAME + (py * 2) * F_DPITCH + px * 2 + F_DOFF;
     int l[9];
@@ -419,15 +439,24 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        l[dy * 3 + dx] = lab[l0 + dy * F_LPITCH + dx];
-        d[dy * 3 + dx] = p.use_depth ? dn[d0 + dy * F_DPITCH + dx] : 0.f;
+        l[dy * 3 + dx] = min((int)lab[l0 + dy * F_LPITCH + dx], p.ncls);
+        float dv = 0.f;
+        if (p.use_depth) {
+          const float v = __fmul_rn(__fadd_rn(dn[d0 + dy * F_DPITCH + dx], neg_mean), inv_std);
+          dv = msk[l0 + dy * F_LPITCH + dx] ? v : __fmul_rn(v, 0.0f);
+        }
+        d[dy * 3 + dx] = dv;
       }
-    // depth planes: 9 taps x 16 FFMA with constant-bank weights
+    // depth planes: 9 taps x 16 FFMA with constant-bank weights (uniform-register operands).  Packed FFMA2 with the
+    // weights read from shared memory (broadcast LDS.128) was slower: 0.74 vs 0.69 ms per 16 frames.
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const float* w = c_first_wd + (tap * p.t + f) * 16;
+      const float* w = c_first_wd + (tap * (T > 0 ? T : p.t) + f) * 16;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = fmaf(d[tap], w[j], acc[j]);
+      for (int j = 0; j < 8; ++j) {
+        acc[j].x = fmaf(d[tap], w[2 * j], acc[j].x);
+        acc[j].y = fmaf(d[tap], w[2 * j + 1], acc[j].y);
+      }
     }
     // label planes: label maps are piecewise constant, so the 3x3 window of a frame is usually one label:
     // then the nine table rows collapse into one pre-summed row (4 instead of 36 128-bit shared loads).
@@ -439,7 +468,8 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 a = row[q];
-        acc[q * 4 + 0] += a.x; acc[q * 4 + 1] += a.y; acc[q * 4 + 2] += a.z; acc[q * 4 + 3] += a.w;
+        acc[2 * q] = __fadd2_rn(acc[2 * q], make_float2(a.x, a.y));
+        acc[2 * q + 1] = __fadd2_rn(acc[2 * q + 1], make_float2(a.z, a.w));
       }
     } else {
 #pragma unroll
@@ -448,7 +478,8 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 a = row[q];
-          acc[q * 4 + 0] += a.x; acc[q * 4 + 1] += a.y; acc[q * 4 + 2] += a.z; acc[q * 4 + 3] += a.w;
+          acc[2 * q] = __fadd2_rn(acc[2 * q], make_float2(a.x, a.y));
+          acc[2 * q + 1] = __fadd2_rn(acc[2 * q + 1], make_float2(a.z, a.w));
         }
       }
     }
@@ -459,9 +490,11 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       store4_any(p.out, p.out_lo, o + q * 4,
-                 make_float4(fmaxf(acc[q * 4 + 0], 0.f), fmaxf(acc[q * 4 + 1], 0.f), fmaxf(acc[q * 4 + 2], 0.f),
-                             fmaxf(acc[q * 4 + 3], 0.f)),
+                 make_float4(fmaxf(acc[2 * q].x, 0.f), fmaxf(acc[2 * q].y, 0.f), fmaxf(acc[2 * q + 1].x, 0.f),
+                             fmaxf(acc[2 * q + 1].y, 0.f)),
                  p.split != 0);
+  }
+  __syncthreads();                 // every thread is done with this staging buffer before it is refilled
   }
 }
 
@@ -1499,7 +1532,7 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         p.out = a.ptr(c.out.buf, 0); p.out_lo = a.ptr_lo(c.out.buf, 0); p.split = split;
         p.b = b; p.t = net->num_inputs; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2;
         p.ncls = net->num_classes; p.use_depth = net->use_depth; p.mean = net->depth_mean; p.std = net->depth_std;
-        const size_t smem = net->first_tab_floats * 4 + (size_t)p.t * (F_DFRAME * 4 + 2 * F_LFRAME) + 256;
+        const size_t smem = net->first_tab_floats * 4 + 2 * (size_t)p.t * (F_DFRAME * 4 + 2 * F_LFRAME) + 256;   // two staging buffers
         {
           const size_t lut_n = (size_t)9 * p.t * (p.ncls + 1) * 16, wd_n = (size_t)9 * p.t * 16;
           PF_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_first_wd, net->first_tab_dev + lut_n, (wd_n + 16) * sizeof(float), 0,
@@ -1507,12 +1540,18 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         }
         static bool attr_set = false;
         if (!attr_set) {
-          PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
           attr_set = true;
         }
         PF_REQUIRE(smem <= 160 * 1024, PF_EINVAL, "pf_bgnet_forward: first-conv tables too large");
-        dim3 grid(cdiv(p.Ho, F_TH) * cdiv(p.Wo, F_TW), b);
-        first_conv_kernel<<<grid, F_TH * F_TW, smem, st>>>(p);
+        const int total_tiles = cdiv(p.Ho, F_TH) * cdiv(p.Wo, F_TW) * b;
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        const int grid = total_tiles < kNumSMs * per_sm ? total_tiles : kNumSMs * per_sm;   // persistent: whole waves
+        if (p.t == 3) first_conv_kernel<3><<<grid, F_TH * F_TW, smem, st>>>(p);
+        else first_conv_kernel<0><<<grid, F_TH * F_TW, smem, st>>>(p);
         PF_CHECK_CUDA(cudaGetLastError());
         break;
       }
