@@ -410,15 +410,22 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
   tc::mbar_wait(bar0 + 8u * st, (uint32_t)((k >> 1) & 1));
   // No conversion pass over the staged window (it was a third of the kernel's instructions, ncu source view): the taps
   // clamp the label to the zero row (ids >= num_classes, bg_model.py:54-55) and normalise / mask the depth
-  // (bg_model.py:50-51,67-68) as they read.  Outside the image TMA filled zeros: mask 0 zeroes the depth term, but
-  // label 0 is a real class, so tiles on the image border first overwrite their out-of-image labels with the zero row.
+  // (bg_model.py:50-51,67-68) as they read.  Tiles on the image border first patch their out-of-image positions (label :=
+  // zero row, mask := 0, depth := 0): TMA zero-fills columns outside the image, but label 0 is a real class, and the
+  // rows above / below an image are the neighbouring frame's rows in the (W, H * frames) tensor maps.
   if (iy0 < 0 || ix0 < 0 || iy0 + F_IH > p.H || ix0 + F_IW > p.W) {           // tile-uniform
     for (int i = tid; i < p.t * F_IH * F_IW; i += blockDim.x) {
       const int f = i / (F_IH * F_IW);
       const int r = i - f * (F_IH * F_IW);
       const int hy = r / F_IW, hx = r - hy * F_IW;
       const int iy = iy0 + hy, ix = ix0 + hx;
-      if (!(iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)) lab[f * F_LFRAME + hy * F_LPITCH + hx + F_LOFF] = (uint8_t)p.ncls;
+      if (!(iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)) {
+        lab[f * F_LFRAME + hy * F_LPITCH + hx + F_LOFF] = (uint8_t)p.ncls;
+        if (p.use_depth) {         // rows above / below the image are the neighbouring frame's rows in the (W, H * frames) maps
+          msk[f * F_LFRAME + hy * F_LPITCH + hx + F_LOFF] = 0;
+          dn[f * F_DFRAME + hy * F_DPITCH + hx + F_DOFF] = 0.f;
+        }
+      }
     }
     __syncthreads();
   }
