@@ -494,12 +494,10 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
   const int oy = oy0 + py, ox = ox0 + px;
   if (oy < p.Ho && ox < p.Wo) {
     const size_t o = (((size_t)img * p.Ho + oy) * p.Wo + ox) * 16;
+    float v[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      store4_any(p.out, p.out_lo, o + q * 4,
-                 make_float4(fmaxf(acc[2 * q].x, 0.f), fmaxf(acc[2 * q].y, 0.f), fmaxf(acc[2 * q + 1].x, 0.f),
-                             fmaxf(acc[2 * q + 1].y, 0.f)),
-                 p.split != 0);
+    for (int j = 0; j < 8; ++j) { v[2 * j] = fmaxf(acc[j].x, 0.f); v[2 * j + 1] = fmaxf(acc[j].y, 0.f); }
+    store16_any(p.out, p.out_lo, o, v, p.split != 0);
   }
   __syncthreads();                 // every thread is done with this staging buffer before it is refilled
   }

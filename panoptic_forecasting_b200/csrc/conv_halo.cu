@@ -504,10 +504,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
           reinterpret_cast<uint2*>(h)[i] = th;
           reinterpret_cast<uint2*>(l)[i] = tl;
         }
-        uint4* oh = reinterpret_cast<uint4*>(L.out_hi + pix + n);
-        uint4* ol = reinterpret_cast<uint4*>(L.out_lo + pix + n);
-        oh[0] = h[0]; oh[1] = h[1];
-        ol[0] = l[0]; ol[1] = l[1];
+        // one 256-bit store per plane: the pixel's 16 channels are one 32-byte sector (two 128-bit stores wrote each
+        // sector in halves)
+        st_global_256(L.out_hi + pix + n, h[0], h[1]);
+        st_global_256(L.out_lo + pix + n, l[0], l[1]);
       };
       if (L.fold) {
         // six 16-column pieces per 16 output channels: (hi, lo) parts of the dx = 0, 1, 2 blocks.  Output column x takes

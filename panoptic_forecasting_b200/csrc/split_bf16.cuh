@@ -58,6 +58,31 @@ __device__ __forceinline__ void store4_any(void* base, void* base_lo, size_t off
   }
 }
 
+// One 256-bit global store (sm_100: STG.E.256): a whole 32-byte sector per lane, e.g. the 16 bf16 channels of one pixel
+// of one plane.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+// 16 consecutive channels starting at a multiple of 16: fp32 (four 128-bit stores) or one 256-bit store per bf16 plane
+__device__ __forceinline__ void store16_any(void* base, void* base_lo, size_t off, const float* v, bool split) {
+  if (!split) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    return;
+  }
+  uint2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_store4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), &h[i], &l[i]);
+  st_global_256(reinterpret_cast<__nv_bfloat16*>(base) + off, make_uint4(h[0].x, h[0].y, h[1].x, h[1].y),
+                make_uint4(h[2].x, h[2].y, h[3].x, h[3].y));
+  st_global_256(reinterpret_cast<__nv_bfloat16*>(base_lo) + off, make_uint4(l[0].x, l[0].y, l[1].x, l[1].y),
+                make_uint4(l[2].x, l[2].y, l[3].x, l[3].y));
+}
+
 // 8 consecutive channels (128-bit loads/stores on the bf16 planes)
 __device__ __forceinline__ void load8_any(const void* base, const void* base_lo, size_t off, bool split, float* v) {
   if (!split) {
