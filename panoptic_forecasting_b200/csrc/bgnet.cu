@@ -585,36 +585,75 @@ struct UpParams {
   float sh, sw;
 };
 
-// grid = (ceil(Wo * groups / 256), Ho, b): one thread per (output pixel, 8-channel group), 32-bit index math only
-// (the first version's three 64-bit div/mod per thread made the kernel instruction-bound at 1.7 TB/s).
+// grid = (ceil(ceil(Wo / 8) * groups / 256), Ho, b): one thread per (run of 8 output pixels of a row, 8-channel group).
+// Vertical interpolation first, per SOURCE column, and the two columns a pixel needs are carried along the run: at x2
+// upsampling a new source column is needed every other output pixel, so a pixel costs about 2 instead of 8 128-bit
+// loads and a quarter of the unpack / index arithmetic (the one-pixel-per-thread version executed 373 instructions per
+// thread and was issue-bound at 2.5 TB/s: ncu, 245 M warp instructions for the 1/8 -> 1/4 resolution step).
+// Weights follow ATen's area_pixel_compute_source_index (align_corners=True); the association
+// hx * (hy v00 + ly v10) + lx * (hy v01 + ly v11) differs from ATen's by rounding only.
+constexpr int kUpRun = 8;
 __global__ void __launch_bounds__(256) upsample_bilinear_kernel(UpParams p) {
   const bool sp = p.split != 0;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.Wo * p.c4_total) return;
-  const int x = idx / p.c4_total;
-  int c = (idx - x * p.c4_total) * 8;
+  const int runs = (p.Wo + kUpRun - 1) / kUpRun;
+  if (idx >= runs * p.c4_total) return;
+  const int run = idx / p.c4_total;
+  int c = (idx - run * p.c4_total) * 8;
   const int y = blockIdx.y, img = blockIdx.z;
   const int cout = c;
   int s = 0;
   while (c >= p.segs[s].cpad) { c -= p.segs[s].cpad; ++s; }
-  const float fy = p.sh * (float)y, fx = p.sw * (float)x;
-  const int y0 = (int)fy, x0 = (int)fx;
-  const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
-  const float ly = fy - (float)y0, lx = fx - (float)x0;
-  const float hy = 1.f - ly, hx = 1.f - lx;
-  const size_t base = (size_t)img * p.in_img[s] + c;
+  const float fy = p.sh * (float)y;
+  const int y0 = (int)fy;
+  const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, hy = 1.f - ly;
   const int cs = p.segs[s].cstride;
   const void* bh = p.segs[s].base;
   const void* bl = p.segs[s].base_lo;
-  const int r0 = y0 * p.Wi, r1 = y1 * p.Wi;
-  float v00[8], v01[8], v10[8], v11[8], o[8];
-  load8_any(bh, bl, base + (size_t)(r0 + x0) * cs, sp, v00);
-  load8_any(bh, bl, base + (size_t)(r0 + x1) * cs, sp, v01);
-  load8_any(bh, bl, base + (size_t)(r1 + x0) * cs, sp, v10);
-  load8_any(bh, bl, base + (size_t)(r1 + x1) * cs, sp, v11);
+  const size_t row0 = (size_t)img * p.in_img[s] + c + (size_t)y0 * p.Wi * cs;
+  const size_t row1 = (size_t)img * p.in_img[s] + c + (size_t)y1 * p.Wi * cs;
+  auto column = [&](int cx, float* t) {                     // vertically interpolated source column cx
+    float a[8], b_[8];
+    load8_any(bh, bl, row0 + (size_t)cx * cs, sp, a);
+    load8_any(bh, bl, row1 + (size_t)cx * cs, sp, b_);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) o[k] = hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]);
-  store8_any(p.out, p.out_lo, (size_t)img * p.out_img + (size_t)(y * p.Wo + x) * p.out_cs + cout, o, sp);
+    for (int k = 0; k < 8; ++k) t[k] = hy * a[k] + ly * b_[k];
+  };
+  float tl[8], tr[8], o[8];
+  int cl = -1, cr = -1;
+  const int xs = run * kUpRun;
+  size_t out_off = (size_t)img * p.out_img + ((size_t)y * p.Wo + xs) * p.out_cs + cout;
+#pragma unroll
+  for (int i = 0; i < kUpRun; ++i, out_off += p.out_cs) {
+    const int x = xs + i;
+    if (x >= p.Wo) break;
+    const float fx = p.sw * (float)x;
+    const int x0 = (int)fx;
+    const int x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
+    const float lx = fx - (float)x0, hx = 1.f - lx;
+    if (x0 != cl) {
+      if (x0 == cr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tl[k] = tr[k];
+      } else {
+        column(x0, tl);
+      }
+      cl = x0;
+    }
+    if (x1 != cr) {
+      if (x1 == cl) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tr[k] = tl[k];
+      } else {
+        column(x1, tr);
+      }
+      cr = x1;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = hx * tl[k] + lx * tr[k];
+    store8_any(p.out, p.out_lo, out_off, o, sp);
+  }
 }
 
 // K5: fused bilinear(align_corners) x4 upsample + argmax (hardnet.py:373-377 + bg_model.py:98).
@@ -1601,7 +1640,7 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         p.c4_total = ctot / 8; p.split = split;
         p.sh = p.Ho > 1 ? (float)(p.Hi - 1) / (float)(p.Ho - 1) : 0.f;
         p.sw = p.Wo > 1 ? (float)(p.Wi - 1) / (float)(p.Wo - 1) : 0.f;
-        upsample_bilinear_kernel<<<dim3(cdiv(p.Wo * p.c4_total, 256), p.Ho, b), 256, 0, st>>>(p);
+        upsample_bilinear_kernel<<<dim3(cdiv(cdiv(p.Wo, kUpRun) * p.c4_total, 256), p.Ho, b), 256, 0, st>>>(p);
         PF_CHECK_CUDA(cudaGetLastError());
         break;
       }
