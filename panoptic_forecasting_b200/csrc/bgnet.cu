@@ -718,7 +718,7 @@ __global__ void upsample_argmax_kernel(const float* __restrict__ q, int b, int n
 
 // Strip variant for the usual x4 case (3*sw < 1, fw % 4 == 0): one thread = 4 consecutive output
 // pixels of a row; they touch at most 3 source columns x 2 rows, loaded once (18 instead of 48 LDG.128).
-// Same interpolation arithmetic as upsample_argmax_kernel (bit-identical logits).
+// Vertical interpolation first (once per source column): same weights as upsample_argmax_kernel, sums associated differently.
 // AMAX: channel 15 of every source pixel holds its own argmax (written by the head conv's epilogue).  If the six
 // source pixels a strip touches agree on class c, then c maximises every convex combination of them (first-maximum
 // ties included), so the strip is c without any interpolation; label maps are piecewise constant, so that is the
@@ -782,17 +782,21 @@ __global__ void __launch_bounds__(256) upsample_argmax_strip_kernel(const float*
     float4 t0[3], t1[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { t0[c] = __ldg(p0[c] + k); t1[c] = __ldg(p1[c] + k); }
+    float4 col[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      col[c] = make_float4(hy * t0[c].x + ly * t1[c].x, hy * t0[c].y + ly * t1[c].y, hy * t0[c].z + ly * t1[c].z,
+                           hy * t0[c].w + ly * t1[c].w);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 a = a1[j] ? t0[1] : t0[0];
-      const float4 b_ = b2[j] ? t0[2] : (b1[j] ? t0[1] : t0[0]);
-      const float4 c_ = a1[j] ? t1[1] : t1[0];
-      const float4 d = b2[j] ? t1[2] : (b1[j] ? t1[1] : t1[0]);
+      // vertical interpolation once per source column (shared by the strip's pixels), then the horizontal blend
+      const float4 a = a1[j] ? col[1] : col[0];
+      const float4 b_ = b2[j] ? col[2] : (b1[j] ? col[1] : col[0]);
       float v[4];
-      v[0] = hy * (hx[j] * a.x + lx[j] * b_.x) + ly * (hx[j] * c_.x + lx[j] * d.x);
-      v[1] = hy * (hx[j] * a.y + lx[j] * b_.y) + ly * (hx[j] * c_.y + lx[j] * d.y);
-      v[2] = hy * (hx[j] * a.z + lx[j] * b_.z) + ly * (hx[j] * c_.z + lx[j] * d.z);
-      v[3] = hy * (hx[j] * a.w + lx[j] * b_.w) + ly * (hx[j] * c_.w + lx[j] * d.w);
+      v[0] = hx[j] * a.x + lx[j] * b_.x;
+      v[1] = hx[j] * a.y + lx[j] * b_.y;
+      v[2] = hx[j] * a.z + lx[j] * b_.z;
+      v[3] = hx[j] * a.w + lx[j] * b_.w;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = k * 4 + e;
