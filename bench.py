@@ -302,7 +302,7 @@ def main():
     # DRAM traffic per step from the committed ncu capture of this same command (profiles/, batch 16 only)
     traffic_b = traffic_a = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_v13_traffic_per_step.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_v14_traffic_per_step.json")))
         if tr.get("batch") == B:
             ks = tr["per_step"]
             tot = lambda pred: sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in ks.items() if pred(k))
@@ -311,7 +311,7 @@ def main():
     except Exception:
         pass
     roof["traffic"] = traffic_b
-    roof["traffic_note"] = "bytes per step (all Stage B kernels), ncu dram__bytes_read+write, profiles/r1_v13_traffic_per_step.json"
+    roof["traffic_note"] = "bytes per step (all Stage B kernels), ncu dram__bytes_read+write, profiles/r1_v14_traffic_per_step.json"
     a_gbs = STAGE_A_BYTES_PER_FRAME * B / (warp_ms * 1e-3) / 1e9
     roof_a = {"bound": "hbm", "kernel": "pf_zsplat_forward_frames (points + resolve)", "achieved": a_gbs,
               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a_gbs / peaks["hbm_gbs"], "traffic": traffic_a,
