@@ -7,7 +7,7 @@
 //
 // HBM-bound byte work: 8 B (int64 background; 1 B for the uint8 variant) + 4 B depth + 1 B mask in, 8 B out per
 // pixel = 21 B (14 B).  Work decomposition: one WARP owns a 128-pixel segment of one image row, one lane 4
-// consecutive pixels (128-bit loads/stores).  The warp culls the instance list against its segment with one
+// consecutive pixels (256-bit loads/stores of the int64 maps, 128-bit of the depth).  The warp culls the instance list against its segment with one
 // ballot per 32 instances (lane j tests instance j: exact row test, conservative column window) and broadcasts
 // the survivors' parameters by shuffle, so pixels outside every box cost no per-instance work and nothing is
 // staged in shared memory.  The row coordinate (iy, floor, weights) is computed once per (warp, instance).
@@ -36,6 +36,7 @@ struct MergeParams {
   const int* inst_begin;         // [b + 1]
   long long* out;                // [b,H,W]
   int H, W, mh, mw, ulbr, bg_u8, segs_per_row;
+  int vec;                       // W % 4 == 0 and every per-pixel pointer aligned for the 4-pixel vector accesses
 };
 
 // one axis of model_utils.paste_mask + ATen's unnormalize: pixel centre -> source coordinate
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kMergeThreads) panoptic_merge_kernel(const Mer
   const int xs = (int)(seg - (long long)y * p.segs_per_row) * kSegPx;
   const int x = xs + lane * 4;
   const size_t g0 = ((size_t)bi * p.H + y) * p.W + x;
-  const bool vec = (p.W & 3) == 0;                                               // then x < W implies x + 3 < W
+  const bool vec = p.vec != 0;                                                   // W % 4 == 0: x < W implies x + 3 < W
   const bool zmode = p.depths != nullptr && p.bg_depth != nullptr;               // fg_model.py:582
 
   long long label[4];
@@ -72,9 +73,9 @@ __global__ void __launch_bounds__(kMergeThreads) panoptic_merge_kernel(const Mer
         }
       } else {
         const long long* s = reinterpret_cast<const long long*>(p.background) + g0;
-        if (vec) {
-          const longlong2 a = __ldcs(reinterpret_cast<const longlong2*>(s)), c = __ldcs(reinterpret_cast<const longlong2*>(s) + 1);
-          label[0] = a.x; label[1] = a.y; label[2] = c.x; label[3] = c.y;
+        if (vec) {                                                              // 4 x int64 = one 256-bit load (sm_100)
+          asm volatile("ld.global.cs.v4.b64 {%0, %1, %2, %3}, [%4];"
+                       : "=l"(label[0]), "=l"(label[1]), "=l"(label[2]), "=l"(label[3]) : "l"(s));
         } else {
           for (int q = 0; q < 4; ++q) if (x + q < p.W) label[q] = s[q];
         }
@@ -173,9 +174,9 @@ __global__ void __launch_bounds__(kMergeThreads) panoptic_merge_kernel(const Mer
   }
   if (x < p.W) {
     long long* d = p.out + g0;
-    if (vec) {
-      __stcs(reinterpret_cast<longlong2*>(d), make_longlong2(label[0], label[1]));
-      __stcs(reinterpret_cast<longlong2*>(d) + 1, make_longlong2(label[2], label[3]));
+    if (vec) {                                                                  // one 256-bit store: a full sector per lane
+      asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(d), "l"(label[0]), "l"(label[1]), "l"(label[2]), "l"(label[3])
+                   : "memory");
     } else {
       for (int q = 0; q < 4; ++q) if (x + q < p.W) d[q] = label[q];
     }
@@ -242,6 +243,9 @@ extern "C" int pf_panoptic_merge(const void* background_dev, int background_is_u
   p.out = reinterpret_cast<long long*>(out_seg_dev);
   p.H = H; p.W = W; p.mh = mh; p.mw = mw; p.ulbr = use_bbox_ulbr ? 1 : 0;
   p.segs_per_row = cdiv(W, kSegPx);
+  auto aligned = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<size_t>(q) & (a - 1)) == 0; };
+  p.vec = ((W & 3) == 0 && aligned(background_dev, background_is_u8 ? 4 : 32) && aligned(bg_depth_dev, 16) &&
+           aligned(bg_depth_mask_dev, 4) && aligned(out_seg_dev, 32)) ? 1 : 0;
   const long long segs = (long long)p.segs_per_row * H;
   panoptic_merge_kernel<<<dim3((unsigned)((segs + kMergeWarps - 1) / kMergeWarps), b), kMergeThreads, 0, (cudaStream_t)stream>>>(p);
   PF_CHECK_CUDA(cudaGetLastError());
