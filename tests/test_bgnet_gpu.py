@@ -146,3 +146,21 @@ def test_full_size_properties(pf_lib, bg_shapes):
     assert torch.equal(m.predict(cu, {})["seg"], out2["seg"])
     ref = bg_oracle.predict(sd, {k: v[:1].long() if k == "seg" else v[:1] for k, v in inp.items()}, (1024, 2048))
     check_against(out_a, ref, rel_tol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_two_input_frames(pf_lib, precision):
+    """num_inputs = 2 (a [16, 24, 3, 3] first conv): the first conv's runtime-frame-count instantiation and every
+    downstream shape, against the oracle."""
+    p = bg_params(precision=precision)
+    p["model"]["num_inputs"] = 2
+    shapes = {k: torch.zeros(v.shape) for k, v in build_model(dict(p)).state_dict().items()}
+    assert tuple(shapes["model.base.0.conv.weight"].shape) == (16, 24, 3, 3)
+    sd = synthetic.make_bg_state_dict(shapes, seed=5)
+    pc = synthetic.make_pc_inputs(2, 2, 64, 192, "R", seed=5)
+    inp = {"seg": pc["seg"].long(), "depth": pc["depth"].clamp(0.1, 200), "depth_mask": pc["depth_mask"]}
+    ref = bg_oracle.predict(sd, inp, None)
+    m = build_model(dict(p, no_gpu=False)).eval()
+    m.load_state_dict(sd)
+    out = m.predict({k: v.cuda() for k, v in inp.items()}, {})
+    check_against(out, ref, rel_tol=REL_TOL if precision == "fp32" else 3e-4)
