@@ -51,6 +51,9 @@ const char* pf_last_error(void);
  * mode); the per-frame mode (only_this_ind=i) is the same call with t=1 on frame i's slices.
  * Ties on depth go to the lowest flattened source index e = replica*t*N + frame*N + v*W + u.
  * ------------------------------------------------------------------------------------- */
+/* Work space: the z-buffers (8 bytes per target cell) of ONE group of batch items -- a slab of at most
+ * PF_ZSPLAT_L2_MB (default 64) MiB, or one item if that is larger, reused by every group so that it stays in
+ * L2 -- plus one bit per output cell.  Sized for the per-frame mode. */
 size_t pf_zsplat_workspace_bytes(int b, int t, int H, int W);
 
 int pf_zsplat_forward(const float* depth_dev, const uint8_t* mask_dev, const uint8_t* seg_dev,
@@ -86,8 +89,26 @@ int pf_zsplat_forward_frames_hop(const float* depth_dev, const uint8_t* mask_dev
                                  float min_depth, float max_depth,
                                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
-/* Same, with HOST buffers: copies inputs to the device, runs, copies seg/depth back and
- * synchronises the stream.  This is the end-to-end call bench.py times as `e2e`. */
+/* Per-frame mode + fused disk hop with PACKED inputs (half the bytes of the reference's formats on the wire):
+ *   depth_code_dev u16 [b,t,H,W]     depth = depth_lut_dev[code]; the caller builds the 65536-entry f32 table with
+ *   depth_lut_dev  f32 [65536]       whatever disparity -> depth formula it uses (the Cityscapes disparity PNGs the
+ *                                    reference's dataset decodes, pc_transform_dataset.py:274, are uint16), so the
+ *                                    result is bit-identical to pf_zsplat_forward_frames_hop on depth = lut[code]
+ *   mask_bits_dev  u8  [b,t,H*W/8]   depth_mask, bit i%8 (LSB first) of byte i/8 of each plane; 16-byte aligned
+ * H*W must be a multiple of 8.  Everything else as pf_zsplat_forward_frames_hop. */
+int pf_zsplat_forward_frames_hop_packed(const uint16_t* depth_code_dev, const float* depth_lut_dev,
+                                        const uint8_t* mask_bits_dev, const uint8_t* seg_dev,
+                                        const float* K_dev, const float* Kinv_dev,
+                                        const float* E_dev, const float* Einv_dev, const float* T_dev,
+                                        int b, int t, int H, int W, const uint8_t* lut_dev,
+                                        uint8_t* out_seg_dev, float* out_depth_dev, uint8_t* out_mask_dev,
+                                        float min_depth, float max_depth,
+                                        void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* pf_zsplat_forward with HOST buffers (convenience / smoke call): allocates device staging, copies the inputs,
+ * runs, copies seg/depth back and synchronises.  Not a throughput path: the pipelined host-buffer front end that
+ * bench.py times as `e2e` is panoptic_forecasting_b200.pipeline.PipelinedForecaster (pinned staging, overlapped
+ * copies) on top of the device-pointer entry points above. */
 int pf_zsplat_forward_host(const float* depth, const uint8_t* mask, const uint8_t* seg,
                            const float* K, const float* Kinv, const float* E, const float* Einv,
                            const float* T, int b, int t, int H, int W, int payload,
@@ -149,7 +170,7 @@ int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* de
 /* number of kernel launches one pf_bgnet_forward enqueues (for bench.py's gpu_launches) */
 int pf_bgnet_launches_per_forward(const pf_bgnet_t* net);
 int pf_zsplat_launches_per_forward(void);
-int pf_zsplat_launches_for(int b, int t, int H, int W);   /* per-frame mode: point kernels run per L2-sized group */
+int pf_zsplat_launches_for(int b, int t, int H, int W);   /* per-frame mode: (points + resolve) per L2-sized group + patch */
 
 /* Per-step device timing (CUDA events recorded on the caller's stream around every step of the
  * next `max_iters` forwards); pf_bgnet_read_profile synchronises on the last event and returns

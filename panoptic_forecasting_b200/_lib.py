@@ -28,6 +28,7 @@ SIGNATURES = {
     "pf_zsplat_forward": (_i, [_vp] * 8 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
     "pf_zsplat_forward_frames": (_i, [_vp] * 8 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
     "pf_zsplat_forward_frames_hop": (_i, [_vp] * 8 + [_i] * 4 + [_vp] * 4 + [_f, _f, _vp, _sz, _vp]),
+    "pf_zsplat_forward_frames_hop_packed": (_i, [_vp] * 9 + [_i] * 4 + [_vp] * 4 + [_f, _f, _vp, _sz, _vp]),
     "pf_zsplat_forward_host": (_i, [_vp] * 8 + [_i] * 5 + [_vp] * 3),
     "pf_zsplat_launches_per_forward": (_i, []),
     "pf_zsplat_launches_for": (_i, [_i, _i, _i, _i]),

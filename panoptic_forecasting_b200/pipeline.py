@@ -28,11 +28,14 @@ class BGForecastPipeline:
         (== t reference PCTransformModel.predict calls with only_this_ind = 0..t-1).
         Returns (seg u8 [b,t,H,W], depth f32 [b,t,H,W]); with fuse_hop=True the depth is already
         disk-hop decoded and a third value, the u8 validity mask, is returned."""
-        depth = inputs['depth']
+        packed = 'depth_code' in inputs
+        depth = inputs['depth_code'] if packed else inputs['depth']
         if not depth.is_cuda:
             raise _lib.PFError("BGForecastPipeline needs CUDA tensors (no CPU fallback)")
         dev = depth.device
         b, t, H, W = depth.shape
+        if packed and not fuse_hop:
+            raise ValueError("packed inputs (depth_code / depth_lut / depth_mask_bits) need fuse_hop=True")
         K = inputs['intrinsics'].to(dev, torch.float32).contiguous()
         E = inputs['extrinsics'].to(dev, torch.float32).contiguous()
         Kinv = (inputs['intrinsics_inv'].to(dev, torch.float32) if 'intrinsics_inv' in inputs
@@ -40,9 +43,19 @@ class BGForecastPipeline:
         Einv = (inputs['extrinsics_inv'].to(dev, torch.float32) if 'extrinsics_inv' in inputs
                 else torch.inverse(E)).contiguous()
         T = inputs['target_T'].to(dev, torch.float32).contiguous()
-        depth_c = depth.to(torch.float32).contiguous()
-        mask = inputs['depth_mask'].contiguous()
-        mask_c = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+        if packed:
+            # pf_zsplat_forward_frames_hop_packed: uint16 depth codes + caller-built table + bit-packed mask
+            if depth.dtype not in (torch.uint16, torch.int16) or inputs['depth_mask_bits'].dtype != torch.uint8:
+                raise TypeError("depth_code must be (u)int16 and depth_mask_bits uint8")
+            depth_c = depth.contiguous()
+            mask_c = inputs['depth_mask_bits'].contiguous()
+            lut_c = inputs['depth_lut'].to(dev, torch.float32).contiguous()
+            if lut_c.numel() != 65536 or mask_c.numel() != b * t * (H * W // 8) or (H * W) % 8:
+                raise ValueError("depth_lut must have 65536 entries and depth_mask_bits b*t*H*W/8 bytes")
+        else:
+            depth_c = depth.to(torch.float32).contiguous()
+            mask = inputs['depth_mask'].contiguous()
+            mask_c = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
         seg_c = inputs['seg'].contiguous()
         if seg_c.dtype != torch.uint8:
             raise TypeError("seg must be uint8")
@@ -53,6 +66,16 @@ class BGForecastPipeline:
         out_depth = torch.empty((b, t, H, W), dtype=torch.float32, device=dev)
         if fuse_hop:
             out_mask = torch.empty((b, t, H, W), dtype=torch.uint8, device=dev)
+            if packed:
+                with torch.cuda.device(dev):
+                    stream = torch.cuda.current_stream(dev).cuda_stream
+                    rc = self._lib.pf_zsplat_forward_frames_hop_packed(
+                        depth_c.data_ptr(), lut_c.data_ptr(), mask_c.data_ptr(), seg_c.data_ptr(), K.data_ptr(),
+                        Kinv.data_ptr(), E.data_ptr(), Einv.data_ptr(), T.data_ptr(), b, t, H, W, None,
+                        out_seg.data_ptr(), out_depth.data_ptr(), out_mask.data_ptr(), float(self.min_depth),
+                        float(self.max_depth), self._ws.data_ptr(), self._ws.numel(), stream)
+                _lib.check(rc, "pf_zsplat_forward_frames_hop_packed")
+                return out_seg, out_depth, out_mask
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev).cuda_stream
                 rc = self._lib.pf_zsplat_forward_frames_hop(
@@ -91,7 +114,7 @@ class BGForecastPipeline:
     def forecast(self, inputs):
         """inputs: the PCTransformModel input dict (pc_transform_model.py:27-32).
         Returns the BGModel.predict dict plus 'warped_seg' / 'warped_depth' / 'warped_mask'."""
-        if self.emulate_disk_hop:
+        if self.emulate_disk_hop or 'depth_code' in inputs:
             seg, d, m = self.warp(inputs, fuse_hop=True)      # hop fused into the resolve kernel
         else:
             seg, depth = self.warp(inputs)

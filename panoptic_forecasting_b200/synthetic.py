@@ -134,6 +134,43 @@ def make_pc_inputs(b=1, t=3, h=1024, w=2048, dist="R", seed=0, steps=(15, 12, 9)
     }
 
 
+CITYSCAPES_BASELINE_M = 0.209313          # stereo baseline: depth = baseline * fx / disparity
+
+
+def disparity_lut(fx=CITYSCAPES_K[0], baseline=CITYSCAPES_BASELINE_M):
+    """65536-entry float32 table code -> depth for Cityscapes-style uint16 disparity PNGs: disparity =
+    (code - 1) / 256 for code > 0, depth = baseline * fx / disparity (computed in float64, rounded once);
+    code 0 (no measurement) and code 1 (zero disparity) map to depth 0."""
+    code = np.arange(65536, dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        depth = baseline * fx / ((code - 1.0) / 256.0)
+    depth[:2] = 0.0
+    return depth.astype(np.float32)
+
+
+def pack_pc_inputs(inputs, lut=None):
+    """Packed form of a PCTransformModel input dict (pf_zsplat_forward_frames_hop_packed): the float depth is
+    replaced by the nearest uint16 disparity code of `lut` (so it becomes a value of the table, as real
+    Cityscapes depth is) and the bool mask by 1 bit per pixel.  Returns (packed dict, unpacked dict whose
+    'depth' is exactly lut[code] -- the same frames in the reference's formats)."""
+    lut = disparity_lut() if lut is None else np.asarray(lut, np.float32)
+    depth = inputs["depth"].cpu().numpy()
+    fx, base = CITYSCAPES_K[0], CITYSCAPES_BASELINE_M
+    with np.errstate(divide="ignore"):
+        code = np.rint(base * fx / depth.astype(np.float64) * 256.0 + 1.0)
+    code = np.clip(np.nan_to_num(code, nan=0.0, posinf=65535.0), 2, 65535).astype(np.uint16)
+    mask = inputs["depth_mask"].cpu().numpy().astype(bool)
+    b, t, h, w = depth.shape
+    bits = np.packbits(mask.reshape(b, t, h * w), axis=-1, bitorder="little")
+    packed = {k: v for k, v in inputs.items() if k not in ("depth", "depth_mask")}
+    packed["depth_code"] = torch.from_numpy(code.view(np.int16))
+    packed["depth_lut"] = torch.from_numpy(lut.copy())
+    packed["depth_mask_bits"] = torch.from_numpy(bits)
+    unpacked = dict(inputs)
+    unpacked["depth"] = torch.from_numpy(lut[code])
+    return packed, unpacked
+
+
 def make_bg_inputs(b=1, t=3, h=512, w=1024, seed=0, device="cpu", label_dtype=torch.int64):
     """Inputs dict for BGModel.predict: labels iid {0..18},
     depth U(0,100), mask = depth > 5."""

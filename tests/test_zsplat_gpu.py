@@ -94,7 +94,7 @@ def test_label_lut_and_no_coords(pf_lib):
 
 
 def test_host_buffer_entry_point(pf_lib):
-    """pf_zsplat_forward_host (the e2e call bench.py times) == device-pointer path == oracle."""
+    """pf_zsplat_forward_host (host-buffer convenience call) == device-pointer path == oracle."""
     npin = with_inverses(synthetic.make_pc_inputs(b=2, t=1, h=64, w=96, dist="U", seed=9))
     ref = pc_transform_oracle.predict(npin)
     c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
@@ -109,6 +109,60 @@ def test_host_buffer_entry_point(pf_lib):
                                        p(oseg), p(odep))
     assert rc == 0, pf_lib.pf_last_error()
     assert_same({"seg": oseg, "depth": odep}, ref)
+
+
+@pytest.mark.parametrize("dist", ["R", "U"])
+@pytest.mark.parametrize("ind", [0, None])
+@pytest.mark.parametrize("shape", [(2, 3, 64, 128), (1, 3, 128, 256), (3, 2, 32, 384), (2, 3, 100, 96), (1, 2, 4, 32)])
+@pytest.mark.parametrize("l2_mb", [None, "1"])
+def test_fast_point_kernel_bit_exact(pf_lib, monkeypatch, dist, ind, shape, l2_mb):
+    """W % 32 == 0, H % 4 == 0 and no result2d: the packed-FFMA2 point kernel with horizontal (warp shuffle) and
+    vertical (in-thread) candidate merging, the slab reused by several groups (PF_ZSPLAT_L2_MB=1: one z-buffer per
+    group, so the call-wide sentinel is patched in after the last group) -- same bits as the oracle, and as the generic
+    kernel (PF_ZSPLAT_NO_FAST=1)."""
+    b, t, h, w = shape
+    if l2_mb is not None:
+        monkeypatch.setenv("PF_ZSPLAT_L2_MB", l2_mb)
+    npin = with_inverses(synthetic.make_pc_inputs(b=b, t=t, h=h, w=w, dist=dist, seed=7 + h))
+    out = run_gpu(npin, ind, return_result2d=False)
+    assert_same(out, pc_transform_oracle.predict(npin, only_this_ind=ind))
+    monkeypatch.setenv("PF_ZSPLAT_NO_FAST", "1")
+    assert_same(run_gpu(npin, ind, return_result2d=False), out)
+
+
+def hop_np(d, mn=0.1, mx=200.0):
+    q = ((torch.from_numpy(d) + 1).clamp(0, 255) * 256).round().numpy().astype(np.uint16)
+    r = torch.from_numpy(q.astype(np.float32)) / 256.0 - 1
+    m = r > 0
+    r[~m] = -1
+    r[m & (r > mx)] = mx
+    r[m & (r < mn)] = mn
+    return r.numpy(), m.numpy()
+
+
+@pytest.mark.parametrize("dist", ["R", "U"])
+@pytest.mark.parametrize("shape", [(2, 3, 64, 128), (2, 3, 40, 96), (2, 3, 30, 72), (1, 3, 256, 512)])
+def test_packed_inputs_bit_exact(pf_lib, bg_shapes, dist, shape):
+    """pf_zsplat_forward_frames_hop_packed (uint16 depth code + table, 1-bit mask) == the reference-format entry
+    point on depth = lut[code] == oracle + disk hop, bit for bit (fast kernel for W % 128 == 0, generic otherwise)."""
+    from conftest import bg_params
+    from panoptic_forecasting_b200.pipeline import BGForecastPipeline
+    b, t, h, w = shape
+    packed, unpacked = synthetic.pack_pc_inputs(synthetic.make_pc_inputs(b=b, t=t, h=h, w=w, dist=dist, seed=3 + w))
+    npin = with_inverses(unpacked)
+    bg = build_model(dict(bg_params(), no_gpu=False)).eval()
+    pipe = BGForecastPipeline(bg)
+    inv = {"intrinsics_inv": torch.from_numpy(npin["intrinsics_inv"]), "extrinsics_inv": torch.from_numpy(npin["extrinsics_inv"])}
+    got_p = [x.cpu().numpy() for x in pipe.warp({k: v.cuda() for k, v in dict(packed, **inv).items()}, fuse_hop=True)]
+    got_u = [x.cpu().numpy() for x in pipe.warp({k: v.cuda() for k, v in dict(unpacked, **inv).items()}, fuse_hop=True)]
+    for a, c in zip(got_p, got_u):
+        assert np.array_equal(a.view(np.uint8), c.view(np.uint8))
+    for ind in range(t):
+        ref = pc_transform_oracle.predict(npin, only_this_ind=ind)
+        d, m = hop_np(ref["depth"])
+        assert np.array_equal(got_p[0][:, ind], ref["seg"])
+        assert np.array_equal(got_p[1][:, ind].view(np.uint32), d.view(np.uint32))
+        assert np.array_equal(got_p[2][:, ind].astype(bool), m)
 
 
 def test_full_size_properties(pf_lib):
