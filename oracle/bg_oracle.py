@@ -47,6 +47,58 @@ def get_link(layer, base_ch, growth_rate, grmul):
     return out_channels, in_channels, link
 
 
+def state_dict_shapes(num_classes=11, num_inputs=3, use_depth=True):
+    """Names and shapes of the reference BGModel's state_dict (418 entries for the bg configs), derived from the
+    topology constants above (hardnet.py:262-339, bg_model.py:17-48) -- so that callers that must not import the
+    product package (bench.py --impl reference on the port) can build seeded weights."""
+    shapes = {}
+    if use_depth:
+        shapes["depth_mean"] = (1,)
+        shapes["depth_std"] = (1,)
+
+    def conv(prefix, cin, cout, k):
+        shapes[prefix + ".conv.weight"] = (cout, cin, k, k)
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            shapes[prefix + ".norm." + n] = (cout,)
+        shapes[prefix + ".norm.num_batches_tracked"] = ()
+
+    def block(prefix, in_ch, gr, n_layers):
+        out_ch = 0
+        for l in range(n_layers):
+            outch, inch, _ = get_link(l + 1, in_ch, gr, GRMUL)
+            conv("%s.layers.%d" % (prefix, l), inch, outch, 3)
+            if l % 2 == 0 or l == n_layers - 1:
+                out_ch += outch
+        return out_ch
+
+    cin0 = (num_classes + (1 if use_depth else 0)) * num_inputs
+    p = "model."
+    conv(p + "base.0", cin0, FIRST_CH[0], 3)
+    conv(p + "base.1", FIRST_CH[0], FIRST_CH[1], 3)
+    conv(p + "base.2", FIRST_CH[1], FIRST_CH[2], 3)
+    conv(p + "base.3", FIRST_CH[2], FIRST_CH[3], 3)
+    idx, ch, skips = 4, FIRST_CH[3], []
+    blks = len(N_LAYERS)
+    for i in range(blks):
+        ch = block(p + "base.%d" % idx, ch, GR[i], N_LAYERS[i])
+        idx += 1
+        if i < blks - 1:
+            skips.append(ch)
+        conv(p + "base.%d" % idx, ch, CH_LIST[i], 1)
+        idx += 1
+        ch = CH_LIST[i]
+        if i < blks - 1:
+            idx += 1                                   # AvgPool2d holds no parameters
+    for j in range(blks - 1):
+        i = blks - 2 - j
+        cat = ch + skips.pop()
+        conv(p + "conv1x1_up.%d" % j, cat, cat // 2, 1)
+        ch = block(p + "denseBlocksUp.%d" % j, cat // 2, GR[i], N_LAYERS[i])
+    shapes[p + "finalConv.weight"] = (num_classes, ch, 1, 1)
+    shapes[p + "finalConv.bias"] = (num_classes,)
+    return shapes
+
+
 def conv_layer(sd, prefix, x, kernel, stride=1):
     """hardnet.py:16-25 in eval mode."""
     x = F.conv2d(x, sd[prefix + ".conv.weight"], None, stride, kernel // 2)

@@ -25,11 +25,13 @@ def pc_predict(inputs, only_this_ind=None):
         depth, mask, T, seg = depth[:, s], mask[:, s], T[:, s], seg[:, s]
     b, t, H, W = depth.shape
     N = H * W
-    vs, us = torch.meshgrid(torch.arange(H, dtype=torch.float), torch.arange(W, dtype=torch.float), indexing="ij")
-    pix = torch.stack([us.reshape(-1), vs.reshape(-1), torch.ones(N)], -1).expand(b, N, 3)
+    dev = depth.device          # CPU for the baseline; bench.py's library_baseline leg runs the same ops on the GPU
+    vs, us = torch.meshgrid(torch.arange(H, dtype=torch.float, device=dev), torch.arange(W, dtype=torch.float, device=dev),
+                            indexing="ij")
+    pix = torch.stack([us.reshape(-1), vs.reshape(-1), torch.ones(N, device=dev)], -1).expand(b, N, 3)
     rays = (torch.inverse(K).reshape(b, 1, 3, 3) @ pix.unsqueeze(-1)).squeeze(-1)          # :51-54
     pc = rays.unsqueeze(1) * depth.reshape(b, t, N, 1)                                      # :55
-    pc = torch.cat([pc, torch.ones(b, t, N, 1)], -1).unsqueeze(-1)                          # :56-59
+    pc = torch.cat([pc, torch.ones(b, t, N, 1, device=dev)], -1).unsqueeze(-1)              # :56-59
     pv = E.view(b, 1, 1, 4, 4) @ pc                                                         # :63
     pt = T.unsqueeze(2) @ pv                                                                # :68
     qc = torch.inverse(E).reshape(b, 1, 1, 4, 4) @ pt                                       # :71
@@ -49,16 +51,16 @@ def pc_predict(inputs, only_this_ind=None):
     zs = z.repeat(1, 4)
     cell = ys * W + xs                                                                      # :117
     Etot = 4 * t * N
-    mn = torch.full((b, N), float("inf")).scatter_reduce_(1, cell, zs, "amin", include_self=True)   # :118
-    e = torch.arange(Etot).expand(b, Etot)
+    mn = torch.full((b, N), float("inf"), device=dev).scatter_reduce_(1, cell, zs, "amin", include_self=True)   # :118
+    e = torch.arange(Etot, device=dev).expand(b, Etot)
     cand = torch.where(zs == mn.gather(1, cell), e, torch.full_like(e, Etot))
-    arg = torch.full((b, N), Etot, dtype=torch.long).scatter_reduce_(1, cell, cand, "amin", include_self=True)
+    arg = torch.full((b, N), Etot, dtype=torch.long, device=dev).scatter_reduce_(1, cell, cand, "amin", include_self=True)
     hit = arg < Etot                                                                        # :120
     src = (arg % (t * N)).clamp_(max=t * N - 1)
     segf = seg.reshape(b, t * N).clone()
     segf[~valid] = 0                                                                        # :133
     out_seg = torch.where(hit, segf.gather(1, src), torch.zeros_like(segf[:, :N]))          # :134
-    out_depth = torch.where(hit, z.gather(1, src), torch.full((b, N), -1.0))                # :136-139
+    out_depth = torch.where(hit, z.gather(1, src), torch.full((b, N), -1.0, device=dev))    # :136-139
     return {"seg": out_seg.view(b, H, W), "depth": out_depth.view(b, H, W)}
 
 

@@ -1,9 +1,10 @@
 """Loader for the UNMODIFIED reference package (test infrastructure only).
 
-Imports ``panoptic_forecasting`` straight from ``/root/reference`` (read-only,
-only present in the build container -- never on the GPU box) so the oracle
-restatement in this directory can be pinned against the reference's own code
-and so ``tests/golden/make_golden.py`` can generate committed fixtures.
+Imports the reference's ``panoptic_forecasting`` either from ``/root/reference`` (read-only, only
+present in the build container) or from ``baseline/_ref`` (the offline ``pip install --target``
+of the same tree: git-ignored, but it travels to the GPU box), so that the oracle restatement in
+this directory can be pinned against the reference's own code, ``tests/golden/make_golden.py`` can
+generate committed fixtures, and ``bench.py --impl reference`` can time the reference itself.
 
 Two shims are needed:
   * empty stub modules for ``cityscapesscripts`` / ``h5py`` (import-time only
@@ -21,7 +22,17 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("PF_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    for cand in (os.environ.get("PF_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "panoptic_forecasting")):
+            return cand
+    return os.environ.get("PF_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def scatter_min(src, index, dim=-1, out=None, dim_size=None):

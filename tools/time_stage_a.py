@@ -22,10 +22,7 @@ def main():
     pipe = BGForecastPipeline(bg)
     sets = []
     for s in range(2):
-        hs = bench.host_input_sets(1, batch, s, dist)[0]
-        if packed:
-            inv = {k: v for k, v in hs.items() if k.endswith("_inv")}
-            hs = dict(synthetic.pack_pc_inputs({k: v for k, v in hs.items() if not k.endswith("_inv")})[0], **inv)
+        hs = bench.host_input_sets(1, batch, s, dist, synthetic, packed=True)[0][1 if packed else 0]
         sets.append({k: v.to(dev) for k, v in hs.items()})
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for i in range(3):

@@ -37,7 +37,7 @@ def main():
     pipe = BGForecastPipeline(bg)
     for dist in ("R", "U"):
         for seed in (0, 1, 2):
-            hs = bench.host_input_sets(1, batch, seed, dist)[0]
+            hs = bench.host_input_sets(1, batch, seed, dist)[0][0]
             inp = {k: v.to(dev) for k, v in hs.items()}
             print("dist %s seed %d batch %d precision %s" % (dist, seed, batch, precision))
             seg, depth = timed("warp", lambda: pipe.warp(inp))
