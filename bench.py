@@ -440,8 +440,9 @@ def main():
 
     from panoptic_forecasting_b200 import _lib, synthetic
     from panoptic_forecasting_b200.models import build_model
-    from panoptic_forecasting_b200.pipeline import BGForecastPipeline, PipelinedForecaster
+    from panoptic_forecasting_b200.pipeline import BGForecastPipeline, PipelinedForecaster, bind_to_gpu_numa
 
+    numa_cores = bind_to_gpu_numa(local_rank) if world > 1 else []   # before any pinned allocation
     L = _lib.lib()
     bg = build_model(bg_params(args.precision)).eval()
     bg.load_state_dict(make_state_dict(bg, 0, synthetic))
@@ -649,7 +650,7 @@ def main():
                 "stage_ms_per_step": {"stage_a_warp": warp_ms, "stage_b_net": net_ms,
                                       "profiled_pass": {"convs": conv_ms, "first_conv": first_ms,
                                                         "pool_upsample_head": other_ms, "steps": n_prof}},
-                "latency": latency, "parity": parity,
+                "latency": latency, "parity": parity, "numa_cores_rank0": len(numa_cores),
                 "clocks": clocks, "cpu_baseline": cpu_base, "library_baseline": lib_base}
         print(json.dumps(line))
     if world > 1:

@@ -73,9 +73,7 @@ struct pf_bgnet {
   // first conv (labels -> 16 ch) tables: lut[tap][frame][class+1][16], wd[tap][frame][16], bias[16]
   float* first_tab_dev = nullptr;
   size_t first_tab_floats = 0;
-  void* first_maps_dev = nullptr;            // TMA tensor maps of the caller's labels / depth / mask tensors
-  const void *fm_labels = nullptr, *fm_depth = nullptr, *fm_mask = nullptr;
-  int fm_b = 0, fm_H = 0, fm_W = 0;
+  std::vector<float> first_wd_host;          // first conv: depth-plane weights + bias, passed to the kernel by value
   int launches = 0;
   // tensor-core path (precision 1): packed split-bf16 weights live in ConvDesc-indexed arrays; the
   // TMA tensor maps depend on the arena address and shape, so they are cached per (ws, b, H, W).
@@ -289,10 +287,11 @@ static void build_topology(pf_bgnet* net) {
 constexpr int F_TH = 8, F_TW = 32;
 constexpr int F_IH = F_TH * 2 + 1, F_IW = F_TW * 2 + 1;
 
-// depth-plane weights wd[tap][frame][16] and bias[16] of the first conv live in constant memory (uniform
-// operands of FFMA, no shared-memory traffic); refreshed on the stream before every launch (2 KB D2D).
+// depth-plane weights wd[tap][frame][16] and bias[16] of the first conv are KERNEL PARAMETERS (FirstParams::wd): the
+// parameter space is a constant bank, so they are uniform operands of FFMA with no shared-memory traffic, and every
+// launch carries its own copy -- two nets, or one net on two streams, cannot overwrite each other (a process-wide
+// __constant__ array refreshed per call could).
 constexpr int kFirstMaxT = 8;
-__constant__ float c_first_wd[9 * kFirstMaxT * 16 + 16];
 
 // TMA boxes must start on a 16-byte boundary of the innermost (x) dimension: the window's first column
 // ix0 = 64k - 1 is odd, so the depth box starts 3 pixels earlier and the label / mask boxes 15 pixels earlier.
@@ -309,7 +308,8 @@ struct FirstMaps {
 };
 
 struct FirstParams {
-  const FirstMaps* maps;   // device memory (tensor maps of the caller's input tensors)
+  FirstMaps maps;      // tensor maps of the caller's input tensors, by value (kernel parameter space)
+  float wd[9 * kFirstMaxT * 16 + 16];   // depth-plane weights [tap][frame][16], then bias[16]
   const float* tab;    // lut | wd | bias | lutsum
   void* out;           // NHWC, 16 channels: fp32, or bf16 hi plane
   void* out_lo;        // bf16 lo plane (split storage)
@@ -328,19 +328,19 @@ struct FirstParams {
 // an immediate constant-bank operand of its FFMA (with a runtime frame index each weight first went through a
 // uniform-register load, LDCU c[0x3][UR + imm]: 72 of them per frame in front of 144 FFMAs).  T = 0: runtime p.t.
 template <int T>
-__global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParams p_in) {
-  FirstParams p = p_in;
-  if (T > 0) p.t = T;
+__global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const __grid_constant__ FirstParams p_in) {
+  const FirstParams& p = p_in;             // stays in the parameter space (constant bank; TMA needs the maps' addresses there)
+  const int pt = T > 0 ? T : pt;
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ __align__(8) uint64_t bars[2];
-  const int lut_floats = 9 * p.t * (p.ncls + 1) * 16;
-  const int wd_floats = 9 * p.t * 16;
-  const int sum_floats = p.t * (p.ncls + 1) * 16;
+  const int lut_floats = 9 * pt * (p.ncls + 1) * 16;
+  const int wd_floats = 9 * pt * 16;
+  const int sum_floats = pt * (p.ncls + 1) * 16;
   const int tab_floats = lut_floats + wd_floats + 16 + sum_floats;
   // dynamic smem: 2 x { [depth/dn: t x 17 x 72 f32][labels: t x 17 x 96 u8][mask: t x 17 x 96 u8] } [tables]
   // TMA destinations must be 128-byte aligned: align the dynamic window by hand
   unsigned char* sm0 = smraw + ((128u - ((uint32_t)__cvta_generic_to_shared(smraw) & 127u)) & 127u);
-  const int stage_bytes = p.t * (F_DFRAME * 4 + 2 * F_LFRAME);
+  const int stage_bytes = pt * (F_DFRAME * 4 + 2 * F_LFRAME);
   float* lut = reinterpret_cast<float*>(sm0 + 2 * stage_bytes);
   const float* lutsum = lut + lut_floats + wd_floats + 16;
   const int tid = threadIdx.x;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
   const int tiles_per_img = tiles_x * tiles_y;
   const int total_tiles = tiles_per_img * p.b;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
-  const uint32_t stage_tx = (uint32_t)p.t * F_IH * (F_DPITCH * 4 * (p.use_depth ? 1 : 0) + F_LPITCH * (p.use_depth ? 2 : 1));
+  const uint32_t stage_tx = (uint32_t)pt * F_IH * (F_DPITCH * 4 * (p.use_depth ? 1 : 0) + F_LPITCH * (p.use_depth ? 2 : 1));
   // thread 0: all boxes of tile `tile` into staging buffer `st`
   auto issue = [&](int tile, int st) {
     const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
@@ -356,24 +356,24 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
     const int iy0 = ty * F_TH * 2 - 1, ix0 = tx * F_TW * 2 - 1;
     unsigned char* base = sm0 + st * stage_bytes;
     float* dn = reinterpret_cast<float*>(base);
-    uint8_t* lab = base + p.t * F_DFRAME * 4;
-    uint8_t* msk = lab + p.t * F_LFRAME;
+    uint8_t* lab = base + pt * F_DFRAME * 4;
+    uint8_t* msk = lab + pt * F_LFRAME;
     const uint32_t bar_a = bar0 + 8u * st;
     tc::mbar_expect_tx(bar_a, stage_tx);
-    for (int f = 0; f < p.t; ++f) {
-      const int z = img * p.t + f;
+    for (int f = 0; f < pt; ++f) {
+      const int z = img * pt + f;
       // label / mask planes are fetched as 32-bit words starting 15 pixels left of the window
       const int xw = (ix0 - F_LOFF) >> 2;
       const int xd = ix0 - F_DOFF;
       asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                   ::"r"((uint32_t)__cvta_generic_to_shared(lab + f * F_LFRAME)), "l"(&p.maps->m_label), "r"(bar_a),
+                   ::"r"((uint32_t)__cvta_generic_to_shared(lab + f * F_LFRAME)), "l"(&p.maps.m_label), "r"(bar_a),
                      "r"(xw), "r"(z * p.H + iy0) : "memory");
       if (p.use_depth) {
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                     ::"r"((uint32_t)__cvta_generic_to_shared(dn + f * F_DFRAME)), "l"(&p.maps->m_depth), "r"(bar_a),
+                     ::"r"((uint32_t)__cvta_generic_to_shared(dn + f * F_DFRAME)), "l"(&p.maps.m_depth), "r"(bar_a),
                        "r"(xd), "r"(z * p.H + iy0) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                     ::"r"((uint32_t)__cvta_generic_to_shared(msk + f * F_LFRAME)), "l"(&p.maps->m_mask), "r"(bar_a),
+                     ::"r"((uint32_t)__cvta_generic_to_shared(msk + f * F_LFRAME)), "l"(&p.maps.m_mask), "r"(bar_a),
                        "r"(xw), "r"(z * p.H + iy0) : "memory");
       }
     }
@@ -405,8 +405,8 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
   const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
   unsigned char* sbase = sm0 + st * stage_bytes;
   float* dn = reinterpret_cast<float*>(sbase);
-  uint8_t* lab = sbase + p.t * F_DFRAME * 4;
-  uint8_t* msk = lab + p.t * F_LFRAME;
+  uint8_t* lab = sbase + pt * F_DFRAME * 4;
+  uint8_t* msk = lab + pt * F_LFRAME;
   tc::mbar_wait(bar0 + 8u * st, (uint32_t)((k >> 1) & 1));
   // No conversion pass over the staged window (it was a third of the kernel's instructions, ncu source view): the taps
   // clamp the label to the zero row (ids >= num_classes, bg_model.py:54-55) and normalise / mask the depth
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
   // zero row, mask := 0, depth := 0): TMA zero-fills columns outside the image, but label 0 is a real class, and the
   // rows above / below an image are the neighbouring frame's rows in the (W, H * frames) tensor maps.
   if (iy0 < 0 || ix0 < 0 || iy0 + F_IH > p.H || ix0 + F_IW > p.W) {           // tile-uniform
-    for (int i = tid; i < p.t * F_IH * F_IW; i += blockDim.x) {
+    for (int i = tid; i < pt * F_IH * F_IW; i += blockDim.x) {
       const int f = i / (F_IH * F_IW);
       const int r = i - f * (F_IH * F_IW);
       const int hy = r / F_IW, hx = r - hy * F_IW;
@@ -435,9 +435,9 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
   // issue slot); this kernel is issue-bound (ncu: 472 M warp instructions per 16 frames, 61 % issue-active, no memory stall)
   float2 acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = make_float2(c_first_wd[9 * p.t * 16 + 2 * j], c_first_wd[9 * p.t * 16 + 2 * j + 1]);
+  for (int j = 0; j < 8; ++j) acc[j] = make_float2(p.wd[9 * pt * 16 + 2 * j], p.wd[9 * pt * 16 + 2 * j + 1]);
 #pragma unroll
-  for (int f = 0; f < (T > 0 ? T : p.t); ++f) {
+  for (int f = 0; f < pt; ++f) {
     const int l0 = f * F_LFRAME + (py * 2) * F_LPITCH + px * 2 + F_LOFF;
     const int d0 = f * F_DFRAME + (py * 2) * F_DPITCH + px * 2 + F_DOFF;
     int l[9];
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
     // weights read from shared memory (broadcast LDS.128) was slower: 0.74 vs 0.69 ms per 16 frames.
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const float* w = c_first_wd + (tap * (T > 0 ? T : p.t) + f) * 16;
+      const float* w = p.wd + (tap * pt + f) * 16;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[j].x = fmaf(d[tap], w[2 * j], acc[j].x);
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const FirstParam
     } else {
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const float4* row = reinterpret_cast<const float4*>(lut + ((tap * p.t + f) * (p.ncls + 1) + l[tap]) * 16);
+        const float4* row = reinterpret_cast<const float4*>(lut + ((tap * pt + f) * (p.ncls + 1) + l[tap]) * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 a = row[q];
@@ -1368,7 +1368,6 @@ extern "C" void pf_bgnet_destroy(pf_bgnet_t* net) {
   if (net->zero_bias_dev) cudaFree(net->zero_bias_dev);
   if (net->plan.maps_dev) cudaFree(net->plan.maps_dev);
   if (net->first_tab_dev) cudaFree(net->first_tab_dev);
-  if (net->first_maps_dev) cudaFree(net->first_maps_dev);
   for (auto e : net->prof_ev) cudaEventDestroy(e);
   delete net;
 }
@@ -1416,6 +1415,7 @@ static int upload_conv(pf_bgnet* net, int i, const std::vector<double>& wfold /*
     if (net->first_tab_dev) { cudaFree(net->first_tab_dev); net->first_tab_dev = nullptr; }
     if (!net->first_tab_dev) PF_CHECK_CUDA(cudaMalloc(&net->first_tab_dev, tab.size() * sizeof(float)));
     net->first_tab_floats = tab.size();
+    net->first_wd_host.assign(tab.begin() + lut_n, tab.begin() + lut_n + wd_n + 16);
     PF_CHECK_CUDA(cudaMemcpy(net->first_tab_dev, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
     c.loaded = true;
     return 0;
@@ -1563,18 +1563,9 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         {
           PF_REQUIRE(((size_t)labels_dev & 15) == 0 && ((size_t)depth_dev & 15) == 0 && ((size_t)mask_dev & 15) == 0,
                      PF_EINVAL, "pf_bgnet_forward: labels / depth / mask must be 16-byte aligned");
-          // the maps depend on the caller's pointers: re-encode and upload (stream-ordered) only when they change
-          if (!net->first_maps_dev) PF_CHECK_CUDA(cudaMalloc(&net->first_maps_dev, sizeof(FirstMaps)));
-          if (net->fm_labels != labels_dev || net->fm_depth != depth_dev || net->fm_mask != mask_dev || net->fm_b != b ||
-              net->fm_H != H || net->fm_W != W) {
-            FirstMaps fm;
-            int rc = first_conv_maps(&fm, labels_dev, depth_dev, mask_dev, b * net->num_inputs, H, W, net->use_depth != 0);
-            if (rc) return rc;
-            PF_CHECK_CUDA(cudaMemcpyAsync(net->first_maps_dev, &fm, sizeof(FirstMaps), cudaMemcpyHostToDevice, st));
-            net->fm_labels = labels_dev; net->fm_depth = depth_dev; net->fm_mask = mask_dev;
-            net->fm_b = b; net->fm_H = H; net->fm_W = W;
-          }
-          p.maps = reinterpret_cast<const FirstMaps*>(net->first_maps_dev);
+          // the maps depend on the caller's pointers: encoded per call (host-side, ~1 us each) and passed by value
+          int rc = first_conv_maps(&p.maps, labels_dev, depth_dev, mask_dev, b * net->num_inputs, H, W, net->use_depth != 0);
+          if (rc) return rc;
         }
         p.tab = net->first_tab_dev;
         p.out = a.ptr(c.out.buf, 0); p.out_lo = a.ptr_lo(c.out.buf, 0); p.split = split;
@@ -1582,16 +1573,13 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
         p.ncls = net->num_classes; p.use_depth = net->use_depth; p.mean = net->depth_mean; p.std = net->depth_std;
         const size_t smem = net->first_tab_floats * 4 + 2 * (size_t)p.t * (F_DFRAME * 4 + 2 * F_LFRAME) + 256;   // two staging buffers
         {
-          const size_t lut_n = (size_t)9 * p.t * (p.ncls + 1) * 16, wd_n = (size_t)9 * p.t * 16;
-          PF_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_first_wd, net->first_tab_dev + lut_n, (wd_n + 16) * sizeof(float), 0,
-                                                cudaMemcpyDeviceToDevice, st));
+          const size_t wd_n = (size_t)9 * p.t * 16;
+          PF_REQUIRE(net->first_wd_host.size() == wd_n + 16 && p.t <= kFirstMaxT, PF_ESTATE, "pf_bgnet_forward: first conv not loaded");
+          memcpy(p.wd, net->first_wd_host.data(), (wd_n + 16) * sizeof(float));
         }
-        static bool attr_set = false;
-        if (!attr_set) {
-          PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          attr_set = true;
-        }
+        // the attribute is per device and per function: set it on every launch (a host-side store, no driver round trip)
+        PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         PF_REQUIRE(smem <= 160 * 1024, PF_EINVAL, "pf_bgnet_forward: first-conv tables too large");
         const int total_tiles = cdiv(p.Ho, F_TH) * cdiv(p.Wo, F_TW) * b;
         int per_sm = (int)((227 * 1024) / (smem + 1024));

@@ -16,6 +16,8 @@
 // i overlaps the MMAs of tile i+1.
 // Warp roles (224 threads): warp 0 TMA producer, warps 1 and 6 MMA issuers (alternate chunks; warp 1 owns TMEM),
 // warps 2..5 epilogue.
+#include <atomic>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -696,10 +698,16 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
 }
 
 int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblocks, size_t smem_bytes, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr = true;
+  {
+    // the attribute is per DEVICE: remember which devices have it (bit per device ordinal; thread-safe)
+    static std::atomic<unsigned long long> attr_done{0};
+    int dev = 0;
+    PF_CHECK_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      attr_done.fetch_or(bit, std::memory_order_release);
+    }
   }
   const int total_tiles = L.tiles_x * L.tiles_y * L.batch;
   int gx = kNumSMs / nblocks;

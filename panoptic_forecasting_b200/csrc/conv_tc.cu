@@ -13,6 +13,8 @@
 // bf16 tensor rate -- still ~10x the fp32 SIMT rate.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one lane),
 // warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/split -> global).
+#include <atomic>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -242,10 +244,16 @@ void tc_pick_tiling(int coutpad, int total_tiles, int* ntile, int* nblocks, int*
 
 int launch_conv_tc(const TcLayer& L, const CUtensorMap* maps_dev, int nblocks, int batch, size_t smem_bytes,
                    cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    PF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr = true;
+  {
+    // the attribute is per DEVICE: remember which devices have it (bit per device ordinal; thread-safe)
+    static std::atomic<unsigned long long> attr_done{0};
+    int dev = 0;
+    PF_CHECK_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      attr_done.fetch_or(bit, std::memory_order_release);
+    }
   }
   dim3 grid(L.tiles_x * L.tiles_y, nblocks, batch);
   conv_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(L, maps_dev);

@@ -143,12 +143,20 @@ class BGModel(BaseModel):
         b, t, H, W = inps.shape
         if t != self.num_inputs:
             raise ValueError("expected %d input frames, got %d" % (self.num_inputs, t))
-        labels = inps if inps.dtype == torch.uint8 else inps.clamp(0, 255).to(torch.uint8)
+        if inps.dtype == torch.uint8:
+            labels = inps
+        else:
+            # ids outside [0, 255] (the reference's F.one_hot raises on negatives) take the all-zero one-hot row,
+            # like every id >= num_classes (bg_model.py:54-56) -- never class 0
+            labels = torch.where((inps < 0) | (inps > 255), torch.full_like(inps, 255), inps).to(torch.uint8)
         labels = labels.contiguous()
         depth_c = mask_c = None
         if self.use_depth_inps:
             depth_c = depths.to(torch.float32).contiguous()
             mask_c = depth_masks.contiguous()
+            if mask_c.dtype.is_floating_point:
+                # the reference multiplies by the mask (bg_model.py:68); the kernels take a 0/1 mask
+                raise TypeError("depth_masks must be bool or an integer 0/1 mask, got %s" % mask_c.dtype)
             mask_c = mask_c.view(torch.uint8) if mask_c.dtype == torch.bool else mask_c.to(torch.uint8)
         fh, fw = self.final_size if self.final_size is not None else (H, W)
         nbytes = self._lib.pf_bgnet_workspace_bytes(self._net, b, H, W)

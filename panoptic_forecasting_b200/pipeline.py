@@ -139,6 +139,33 @@ class BGForecastPipeline:
         return out
 
 
+def bind_to_gpu_numa(device_index):
+    """Pins the calling process to the CPU cores NVML reports as local to GPU `device_index` (its NUMA node), so that
+    the pinned staging buffers allocated afterwards are first-touched on that node and host->device copies do not
+    cross the socket interconnect.  With 8 ranks uploading ~35 GB/s each this is what the aggregate rate depends on.
+    Returns the core list (empty if NVML is unavailable or reports nothing)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if visible:
+            ids = [x.strip() for x in visible.split(",") if x.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        cores = [c for c in cores if c in os.sched_getaffinity(0)]
+        if cores:
+            os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return []
+
+
 class PipelinedForecaster:
     """Host-buffer front end for throughput runs: uploads of batch i+1 (copy stream) overlap the
     forecast of batch i (compute stream) and the download of batch i-1's label map.
@@ -148,11 +175,14 @@ class PipelinedForecaster:
     how an export loop over a dataset runs (reference loop: export_cityscapes_segmentation_results.py:75-110).
     """
 
-    def __init__(self, pipe, depth=2):
+    def __init__(self, pipe, depth=3):
         self.pipe = pipe
         self.depth = depth
         self.copy_stream = torch.cuda.Stream()
         self.compute_stream = torch.cuda.Stream()
+        self.down_stream = torch.cuda.Stream()   # label-map download: off the compute stream (0.65 ms per 16-frame batch)
+        self.out_dev = [None] * depth
+        self.computed = [torch.cuda.Event() for _ in range(depth)]
         self.slots = [None] * depth          # device input dicts
         self.out_host = [None] * depth       # pinned uint8 label maps
         self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
@@ -179,10 +209,15 @@ class PipelinedForecaster:
             out = self.pipe.forecast(self.slots[s])
             self.free[s].record(self.compute_stream)
             seg = out['seg']
-            if self.out_host[s] is None or self.out_host[s].shape != seg.shape:
-                self.out_host[s] = torch.empty(seg.shape, dtype=seg.dtype).pin_memory()
+            self.out_dev[s] = seg                              # keeps the tensor alive until its download is enqueued
+            self.computed[s].record(self.compute_stream)
+        if self.out_host[s] is None or self.out_host[s].shape != seg.shape:
+            self.out_host[s] = torch.empty(seg.shape, dtype=seg.dtype).pin_memory()
+        with torch.cuda.stream(self.down_stream):
+            self.down_stream.wait_event(self.computed[s])
             self.out_host[s].copy_(seg, non_blocking=True)
-            self.done[s].record(self.compute_stream)
+            seg.record_stream(self.down_stream)
+            self.done[s].record(self.down_stream)
         self.n_submitted += 1
 
     def collect(self):

@@ -119,15 +119,35 @@ def test_fast_point_kernel_bit_exact(pf_lib, monkeypatch, dist, ind, shape, l2_m
     """W % 32 == 0, H % 4 == 0 and no result2d: the packed-FFMA2 point kernel with horizontal (warp shuffle) and
     vertical (in-thread) candidate merging, the slab reused by several groups (PF_ZSPLAT_L2_MB=1: one z-buffer per
     group, so the call-wide sentinel is patched in after the last group) -- same bits as the oracle, and as the generic
-    kernel (PF_ZSPLAT_NO_FAST=1)."""
+    kernel (the default; PF_ZSPLAT_FAST=1 selects the FFMA2 kernel) in both work-space schemes."""
     b, t, h, w = shape
     if l2_mb is not None:
         monkeypatch.setenv("PF_ZSPLAT_L2_MB", l2_mb)
+    monkeypatch.setenv("PF_ZSPLAT_FAST", "1")
+    monkeypatch.setenv("PF_ZSPLAT_MODE", "slab")
     npin = with_inverses(synthetic.make_pc_inputs(b=b, t=t, h=h, w=w, dist=dist, seed=7 + h))
     out = run_gpu(npin, ind, return_result2d=False)
     assert_same(out, pc_transform_oracle.predict(npin, only_this_ind=ind))
-    monkeypatch.setenv("PF_ZSPLAT_NO_FAST", "1")
+    monkeypatch.delenv("PF_ZSPLAT_FAST")
     assert_same(run_gpu(npin, ind, return_result2d=False), out)
+    monkeypatch.setenv("PF_ZSPLAT_FAST", "1")
+    monkeypatch.setenv("PF_ZSPLAT_MODE", "full")
+    assert_same(run_gpu(npin, ind, return_result2d=False), out)
+
+
+@pytest.mark.parametrize("ind", [1, None])
+@pytest.mark.parametrize("l2_mb", [None, "1"])
+def test_full_mode_bit_exact(pf_lib, monkeypatch, ind, l2_mb):
+    """PF_ZSPLAT_MODE=full: a z-buffer per plane of the call, point kernels per L2-sized group, one resolve at the
+    end with the sentinel known (no patch pass) -- the A/B alternative to the slab scheme."""
+    if l2_mb is not None:
+        monkeypatch.setenv("PF_ZSPLAT_L2_MB", l2_mb)
+    npin = with_inverses(synthetic.make_pc_inputs(b=3, t=3, h=64, w=128, dist="R", seed=31))
+    monkeypatch.setenv("PF_ZSPLAT_MODE", "slab")
+    assert_same(run_gpu(npin, ind, return_result2d=False), pc_transform_oracle.predict(npin, only_this_ind=ind))
+    monkeypatch.setenv("PF_ZSPLAT_MODE", "full")
+    assert_same(run_gpu(npin, ind, return_result2d=False), pc_transform_oracle.predict(npin, only_this_ind=ind))
+    assert_same(run_gpu(npin, ind), pc_transform_oracle.predict(npin, only_this_ind=ind))       # generic kernel + coords
 
 
 def hop_np(d, mn=0.1, mx=200.0):
@@ -142,11 +162,13 @@ def hop_np(d, mn=0.1, mx=200.0):
 
 @pytest.mark.parametrize("dist", ["R", "U"])
 @pytest.mark.parametrize("shape", [(2, 3, 64, 128), (2, 3, 40, 96), (2, 3, 30, 72), (1, 3, 256, 512)])
-def test_packed_inputs_bit_exact(pf_lib, bg_shapes, dist, shape):
+@pytest.mark.parametrize("fast", ["0", "1"])
+def test_packed_inputs_bit_exact(pf_lib, bg_shapes, monkeypatch, dist, shape, fast):
     """pf_zsplat_forward_frames_hop_packed (uint16 depth code + table, 1-bit mask) == the reference-format entry
     point on depth = lut[code] == oracle + disk hop, bit for bit (fast kernel for W % 128 == 0, generic otherwise)."""
     from conftest import bg_params
     from panoptic_forecasting_b200.pipeline import BGForecastPipeline
+    monkeypatch.setenv("PF_ZSPLAT_FAST", fast)
     b, t, h, w = shape
     packed, unpacked = synthetic.pack_pc_inputs(synthetic.make_pc_inputs(b=b, t=t, h=h, w=w, dist=dist, seed=3 + w))
     npin = with_inverses(unpacked)

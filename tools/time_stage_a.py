@@ -1,5 +1,5 @@
 """Dev tool (GPU box): device time of Stage A (pf_zsplat_forward_frames_hop[_packed]) at the bench size.
-usage: python tools/time_stage_a.py [batch] [dist] [packed 0/1] [reps]   (env: PF_ZSPLAT_NO_FAST, PF_ZSPLAT_L2_MB)"""
+usage: python tools/time_stage_a.py [batch] [dist] [packed 0/1] [reps]   (env: PF_ZSPLAT_FAST, PF_ZSPLAT_MODE, PF_ZSPLAT_L2_MB)"""
 import os
 import sys
 
@@ -36,8 +36,8 @@ def main():
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     ts.sort()
-    print("stage A batch %d dist %s packed %d NO_FAST=%s L2_MB=%s: median %.3f ms, min %.3f ms per step" % (
-        batch, dist, packed, os.environ.get("PF_ZSPLAT_NO_FAST"), os.environ.get("PF_ZSPLAT_L2_MB"),
+    print("stage A batch %d dist %s packed %d FAST=%s MODE=%s L2_MB=%s: median %.3f ms, min %.3f ms per step" % (
+        batch, dist, packed, os.environ.get("PF_ZSPLAT_FAST"), os.environ.get("PF_ZSPLAT_MODE"), os.environ.get("PF_ZSPLAT_L2_MB"),
         ts[len(ts) // 2], ts[0]))
 
 
