@@ -330,7 +330,7 @@ struct FirstParams {
 template <int T>
 __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const __grid_constant__ FirstParams p_in) {
   const FirstParams& p = p_in;             // stays in the parameter space (constant bank; TMA needs the maps' addresses there)
-  const int pt = T > 0 ? T : pt;
+  const int pt = T > 0 ? T : p_in.t;
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ __align__(8) uint64_t bars[2];
   const int lut_floats = 9 * pt * (p.ncls + 1) * 16;
