@@ -9,6 +9,11 @@ the skip-if-exists filter that makes an interrupted export resumable (pc_transfo
 Reader side == what BGDataset decodes (data/datasets/bg_dataset.py:172-232): label PNG -> integer
 map, uint16 depth -> d = u16/256 - 1, mask = d > 0, d[~mask] = -1, clamp to [min_depth, max_depth].
 
+The reference's bg dataset reads the depth triplet from ONE HDF5 file (`depths_decompressed_..._val.h5`, key
+`<city>/<seq>/<frame:06d>/<start_fr>`, `[H, W, 3]` uint16: bg_dataset.py:184-196) that an unpublished script repacks from
+the three depth-PNG exports; `repack_depth_pngs_to_h5` is that step and `read_bg_inputs_h5` the matching reader
+(h5lite.py: pure-Python HDF5 subset, h5py is not in the image).
+
 PNG encoding runs on a thread pool so it overlaps the GPU work of the next batches.
 """
 import os
@@ -98,6 +103,33 @@ def read_bg_inputs(label_dirs, depth_dirs, city, seq, frame, min_depth=0.1, max_
     for ld, dd in zip(label_dirs, depth_dirs):
         segs.append(np.array(Image.open(label_path(ld, city, seq, frame)), dtype=np.uint8))
         d, m = decode_depth_u16(np.array(Image.open(depth_path(dd, city, seq, frame))), min_depth, max_depth)
+        deps.append(d)
+        masks.append(m)
+    return {'seg': np.stack(segs), 'depth': np.stack(deps), 'depth_mask': np.stack(masks)}
+
+
+def repack_depth_pngs_to_h5(depth_dirs, items, h5_path):
+    """items: iterable of (city, seq, frame, start_fr).  Stacks the t `..._depths.png` exports of each item (one
+    directory per input frame) into `[H, W, t]` uint16 under `<city>/<seq>/<frame:06d>/<start_fr>`."""
+    from . import h5lite
+    tree = {}
+    for city, seq, frame, start_fr in items:
+        planes = [np.array(Image.open(depth_path(d, city, seq, frame))) for d in depth_dirs]
+        tree.setdefault(city, {}).setdefault(seq, {}).setdefault('%06d' % frame, {})[str(start_fr)] = \
+            np.stack(planes, axis=-1).astype(np.uint16)
+    h5lite.write(h5_path, tree)
+
+
+def read_bg_inputs_h5(label_dirs, h5_file, city, seq, frame, start_fr, min_depth=0.1, max_depth=200.0):
+    """BGDataset.__getitem__ (bg_dataset.py:172-232): t label PNGs + the `[H, W, t]` uint16 depth stack of the HDF5
+    container (an open h5lite.File or a path); same return value as read_bg_inputs."""
+    from . import h5lite
+    f = h5lite.File(h5_file) if isinstance(h5_file, str) else h5_file
+    stack = f['%s/%s/%06d/%s' % (city, seq, frame, start_fr)][()]
+    segs = [np.array(Image.open(label_path(ld, city, seq, frame)), dtype=np.uint8) for ld in label_dirs]
+    deps, masks = [], []
+    for i in range(stack.shape[-1]):
+        d, m = decode_depth_u16(stack[..., i], min_depth, max_depth)
         deps.append(d)
         masks.append(m)
     return {'seg': np.stack(segs), 'depth': np.stack(deps), 'depth_mask': np.stack(masks)}
