@@ -403,7 +403,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_cuda"])
     ap.add_argument("--config", type=int, default=3, choices=[2, 3], help="BASELINE.json configs index (3 = the metric's)")
-    ap.add_argument("--batch", type=int, default=16, help="target frames per step (the reference export uses batch_size 2)")
+    ap.add_argument("--batch", type=int, default=32, help="target frames per step (the reference export uses batch_size 2)")
     ap.add_argument("--ref-frames", type=int, default=2,
                     help="reference arms: target frames actually processed per step (bounded sample of --batch)")
     ap.add_argument("--precision", default=os.environ.get("PF_PRECISION", "tc"), choices=["fp32", "tc"])
