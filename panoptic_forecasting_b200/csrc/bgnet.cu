@@ -1113,7 +1113,7 @@ static bool plan_fold(HaloLayer* T, size_t* smem) {
 // Halo-kernel plan of a 3x3 / stride-1 conv.  Returns 1 when the layer does not fit (caller falls
 // back to the per-tap kernel), 0 on success, <0 / cudaError on failure.
 static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CUtensorMap>* maps, HaloLayer* L,
-                            int* nblocks, size_t* smem, int seg0 = 0, int seg1 = -1) {
+                            int* nblocks, size_t* smem, int seg0 = 0, int seg1 = -1, bool add_patch = false) {
   const ConvDesc& c = net->convs[i];
   if (seg1 < 0) seg1 = (int)c.in.size();
   if (c.exec_stride() != 1) return 1;
@@ -1127,6 +1127,7 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   tc_pick_tiling(c.coutpad, cdiv(io.Wout, 8) * cdiv(io.Hout, 16) * io.b, &ntile, &nb, &stages, &cols, &dummy);
   L->nseg = seg1 - seg0;
   L->ntile = ntile;
+  if (add_patch) L->add_pbytes = (uint32_t)align_up((size_t)kAddPH * kAddPW * (ntile + 4) * 4, 1024);
   int kb = 0;
   bool used[3] = {false, false, false};
   for (int s = 0; s < (int)c.in.size(); ++s) {       // K offsets run over ALL slices; only [seg0, seg1) are read
@@ -1174,7 +1175,11 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
       for (int k = 0; k < L->nseg; ++k) L->seg_w[k] = halo_chunk_width(L->seg_cpad[k]);
     }
   }
-  if (!L->fold && !halo_plan_smem(L, smem)) return 1;
+  if (!L->fold && !halo_plan_smem(L, smem)) {
+    if (!L->add_pbytes) return 1;
+    L->add_pbytes = 0;                                       // no room for the staged patches: per-pixel gathers
+    if (!halo_plan_smem(L, smem)) return 1;
+  }
   if (!L->fold && !no_fold && c.ksize == 3 && L->tap_mask == 0x1FF && ntile == 48 && c.coutpad == 48 && kin >= fold_min_k &&
       !L->resident) {
     // 48 couts whose weights have to be streamed per tile: three folded CTAs of 16 couts with resident weights instead
@@ -1216,6 +1221,10 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     maps->push_back(m);
   }
   *nblocks = nb;
+  {
+    const char* e8 = getenv("PF_HALO_EPI8");               // A/B: second epilogue team for the wide-N layers
+    L->epi8 = (!L->fold && L->ntile >= 64 && !(e8 && e8[0] == '0')) ? 1 : 0;
+  }
   L->Hout = io.Hout; L->Wout = io.Wout; L->batch = io.b;
   L->tiles_x = cdiv(io.Wout, 8); L->tiles_y = cdiv(io.Hout, 16);
   if (L->fold) { L->tiles_x = cdiv(io.Wout, 14); L->tiles_y = cdiv(io.Hout, 8); }
@@ -1284,12 +1293,22 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
       // (2) high-resolution 1x1 over the skip slices + bilinear(ybuf) + bias + ReLU
       TcIo hi = io;                                   // the skip slices live at the output resolution
       hi.Hin = io.Hout; hi.Win = io.Wout;
-      rc = build_halo_layer(net, (int)i, hi, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i], c.up_nseg, (int)c.in.size());
+      const float sh = io.Hout > 1 ? (float)(lo.Hout - 1) / (float)(io.Hout - 1) : 0.f;
+      const float sw = io.Wout > 1 ? (float)(lo.Wout - 1) / (float)(io.Wout - 1) : 0.f;
+      const char* ng = getenv("PF_TC_FUSE_UP_GATHER");       // A/B: per-pixel global gathers instead of the staged patch
+      const bool patch = sh <= 0.5f && sw <= 0.5f && !(ng && ng[0] == '1');   // kAddPH x kAddPW covers a tile at <= 1/2 scale
+      rc = build_halo_layer(net, (int)i, hi, &maps, &P.halos[i], &P.nblocks[i], &P.smem[i], c.up_nseg, (int)c.in.size(), patch);
       PF_REQUIRE(rc == 0, rc == 1 ? PF_EINVAL : rc, "fused conv1x1_up: high-resolution plan failed for %s", c.name.c_str());
       HaloLayer& hl = P.halos[i];
       hl.add_src = lo.out_f32; hl.add_H = lo.Hout; hl.add_W = lo.Wout; hl.add_cs = lo.out_cs; hl.add_img = lo.out_img;
-      hl.add_sh = io.Hout > 1 ? (float)(lo.Hout - 1) / (float)(io.Hout - 1) : 0.f;
-      hl.add_sw = io.Wout > 1 ? (float)(lo.Wout - 1) / (float)(io.Wout - 1) : 0.f;
+      hl.add_sh = sh; hl.add_sw = sw;
+      if (hl.add_pbytes) {
+        CUtensorMap m;
+        rc = halo_encode_add_map(&m, lo.out_f32, lo.out_cs, lo.Wout, lo.Hout, a.b, lo.out_img, hl.ntile);
+        if (rc) return rc;
+        hl.add_map = (int)maps.size();
+        maps.push_back(m);
+      }
       P.use_tc[i] = 3;
       continue;
     }
@@ -1347,10 +1366,13 @@ extern "C" int pf_bgnet_create(pf_bgnet_t** out, int num_classes, int num_inputs
   net->force_simt = fs && fs[0] == '1';
   const char* nh = getenv("PF_TC_NO_HALO");
   net->no_halo = nh && nh[0] == '1';
-  // opt-in (PF_TC_FUSE_UP=1): measured 0.9 % slower than the separate upsample kernel at batch 8 -- the gather
-  // of the low-resolution partial in the epilogue costs more than the upsample kernel + wider 1x1 it replaces
+  // conv1x1_up commuted with the bilinear TransitionUp (default; PF_TC_FUSE_UP=0 selects the separate upsample kernel).
+  // With per-pixel global gathers of the low-resolution partial in the epilogue this was SLOWER than the upsample
+  // kernel + wider 1x1 it replaces (conv1x1_up.3: 746 us vs 347 + 197 per 16 frames); with the partial's patch staged
+  // per tile by TMA (HaloLayer::add_pbytes) the four levels take 0.92 instead of 1.24 ms and 1.4 GB per step of
+  // upsampled tensors are neither written nor read.
   const char* nf = getenv("PF_TC_FUSE_UP");
-  net->fuse_up = precision == 1 && !net->force_simt && !net->no_halo && (nf && nf[0] == '1');
+  net->fuse_up = precision == 1 && !net->force_simt && !net->no_halo && !(nf && nf[0] == '0');
   const char* il = getenv("PF_INTERLEAVED_SLOTS");
   net->compact_slots = !(il && il[0] == '1');
   build_topology(net);

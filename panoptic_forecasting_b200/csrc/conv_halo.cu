@@ -14,8 +14,10 @@
 // high-resolution layers, where a CTA visits many tiles) or STREAMED per (chunk, tap) through a
 // second mbarrier ring.  The fp32 accumulator is double-buffered in TMEM so the epilogue of tile
 // i overlaps the MMAs of tile i+1.
-// Warp roles (224 threads): warp 0 TMA producer, warps 1 and 6 MMA issuers (alternate chunks; warp 1 owns TMEM),
-// warps 2..5 epilogue.
+// Warp roles (352 threads): warp 0 TMA producer, warps 1 and 6 MMA issuers (alternate chunks; warp 1 owns TMEM),
+// warps 2..5 epilogue; for layers with >= 64 output channels per CTA (the 1x1 transition / conv1x1_up layers, which are
+// bound by the epilogue: TMEM reads, bias / ReLU / pool / interpolation, split, stores) warps 7..10 are a second
+// epilogue team that takes every other 16-channel group of the same accumulator rows (HaloLayer::epi8).
 #include <atomic>
 
 #include <cuda.h>
@@ -32,7 +34,7 @@ using namespace tc;
 
 namespace {
 constexpr int kMaxA = 8, kMaxB = 8;
-constexpr int kHaloThreads = 224;      // warp 0 TMA producer, warps 1 and 6 MMA issuers, warps 2..5 epilogue
+constexpr int kHaloThreads = 224, kHaloThreads8 = 352;      // warp 0 TMA producer, warps 1 and 6 MMA issuers, warps 2..5 (+ 7..10: HaloLayer::epi8) epilogue
 
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
@@ -42,6 +44,11 @@ __device__ __forceinline__ uint32_t layout_of(int w) { return w == 64 ? 2u : (w 
 __device__ __forceinline__ uint32_t align1k(uint32_t x) { return (x + 1023u) & ~1023u; }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
 }
 }  // namespace
 
@@ -233,9 +240,10 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
   if (dbg && el) { L.dbg_ts[7] = clock64(); L.dbg_ts[9] = wait_full; L.dbg_ts[10] = wait_tmem; }
 }
 
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxB + 5];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxB + 9];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -251,6 +259,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
   const uint32_t wbar = bar0 + 8u * (2 * kMaxA + 2 * kMaxB);
   auto tmem_full = [&](int a) { return bar0 + 8u * (2 * kMaxA + 2 * kMaxB + 1 + a); };
   auto tmem_empty = [&](int a) { return bar0 + 8u * (2 * kMaxA + 2 * kMaxB + 3 + a); };
+  auto full_p = [&](int a) { return bar0 + 8u * (2 * kMaxA + 2 * kMaxB + 5 + a); };     // additive-term patch (see HaloLayer::add_pbytes)
+  auto empty_p = [&](int a) { return bar0 + 8u * (2 * kMaxA + 2 * kMaxB + 7 + a); };
 
   const int SA = L.stages_a, SB = L.stages_b;
   const uint32_t a_tile = L.a_tile_bytes;          // one plane of one A stage (1024-aligned)
@@ -258,6 +268,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
   const uint32_t w_region = L.resident ? L.w_bytes_total : 0u;
   const uint32_t a_base = smem_base + w_region;
   const uint32_t b_base = a_base + SA * 2 * a_tile;
+  const uint32_t p_base = b_base + (L.resident ? 0u : (uint32_t)SB * b_tile);   // two patch buffers behind the rings
+  const uint32_t p_tx = (uint32_t)(kAddPH * kAddPW) * (uint32_t)(ntile + 4) * 4u;
   const int n0 = blockIdx.y * ntile;
   const int tiles_per_img = L.tiles_x * L.tiles_y;
   const int total_tiles = tiles_per_img * L.batch;
@@ -269,7 +281,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
     for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
     mbar_init(wbar, 1);
     // both MMA warps commit to tmem_full after their last chunk of a tile (a commit only covers the issuing thread's MMAs)
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), L.nchunk >= 2 ? 2 : 1); mbar_init(tmem_empty(a), 4); }
+    const uint32_t nepi = L.epi8 ? 8u : 4u;              // epilogue warps that hand the buffers back
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), L.nchunk >= 2 ? 2 : 1); mbar_init(tmem_empty(a), nepi); }
+    for (int a = 0; a < 2; ++a) { mbar_init(full_p(a), 1); mbar_init(empty_p(a), nepi); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -321,7 +335,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
       }
       // ... and do not read the previous layer's activations before it has completed and flushed.
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      int ia = 0, ib = 0, st = 0;
+      int ia = 0, ib = 0, st = 0, tp = 0;
       uint32_t ph_a = 1;                      // parity to wait on for "stage free"; flips when the ring wraps
       long long wait_acc = 0;
       const int nchunk = L.nchunk;
@@ -330,6 +344,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
         const int r = t - img * tiles_per_img;
         const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
         const int y0 = L.fold ? ty * 8 : ty * 16, x0 = L.fold ? tx * 14 : tx * 8;
+        if (L.add_pbytes) {
+          // the low-resolution patch this tile's epilogue interpolates from (origin = source pixel of the tile's first
+          // row / column, same float arithmetic as the epilogue); out-of-image rows / columns are zero-filled, never read
+          const int pa = tp & 1;
+          mbar_wait(empty_p(pa), ((tp >> 1) & 1) ^ 1);
+          mbar_expect_tx_p(full_p(pa), p_tx, el);
+          tma_load_4d_p(p_base + (uint32_t)pa * L.add_pbytes, maps + L.add_map, full_p(pa), n0,
+                        (int)(L.add_sw * (float)x0), (int)(L.add_sh * (float)y0), img, el);
+          ++tp;
+        }
         for (int j = 0; j < nchunk; ++j, ++ia) {
           const uint32_t code = L.chunk[j];
           const int w = (int)(code & 0xFFu), s = (int)((code >> 12) & 0xFu), c0 = (int)(code >> 16);
@@ -403,9 +427,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp <= 5 || (THREADS > 224 && L.epi8)) {
     // ===== epilogue =====
-    const int q = warp & 3;
+    const int q = warp & 3;                    // TMEM lane quarter (warps 7..10 -> 3, 0, 1, 2)
+    const int team = warp >= 7 ? 1 : 0;        // second team: odd 16-channel groups
     const int m = q * 32 + lane;
     int tc_ = 0;
     long long wait_epi = 0, w0 = 0;
@@ -437,16 +462,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
                                       : (size_t)img * L.out_img_stride + ((size_t)oy * L.Wout + ox) * L.out_cs;
       // bilinear source of the optional additive term (conv1x1_up fused with TransitionUp)
       const float *a00 = nullptr, *a01 = nullptr, *a10 = nullptr, *a11 = nullptr;
+      uint32_t s00 = 0, s01 = 0, s10 = 0, s11 = 0;       // shared-memory addresses of the four source pixels (patch form)
       float aly = 0.f, alx = 0.f;
       if (L.add_src && inside) {
         const float fy = L.add_sh * (float)oy, fx = L.add_sw * (float)ox;
         const int ay0 = (int)fy, ax0 = (int)fx;
         const int ay1 = ay0 + (ay0 < L.add_H - 1 ? 1 : 0), ax1 = ax0 + (ax0 < L.add_W - 1 ? 1 : 0);
         aly = fy - (float)ay0; alx = fx - (float)ax0;
-        const float* ab = L.add_src + (size_t)img * L.add_img;
-        a00 = ab + ((size_t)ay0 * L.add_W + ax0) * L.add_cs; a01 = ab + ((size_t)ay0 * L.add_W + ax1) * L.add_cs;
-        a10 = ab + ((size_t)ay1 * L.add_W + ax0) * L.add_cs; a11 = ab + ((size_t)ay1 * L.add_W + ax1) * L.add_cs;
+        if (L.add_pbytes) {
+          const int py0 = (int)(L.add_sh * (float)(ty * 16)), px0 = (int)(L.add_sw * (float)(tx * 8));
+          const uint32_t pb = p_base + (uint32_t)acc * L.add_pbytes;
+          const uint32_t ps = (uint32_t)(ntile + 4) * 4u;                  // bytes per patch pixel
+          s00 = pb + (uint32_t)((ay0 - py0) * kAddPW + (ax0 - px0)) * ps; s01 = pb + (uint32_t)((ay0 - py0) * kAddPW + (ax1 - px0)) * ps;
+          s10 = pb + (uint32_t)((ay1 - py0) * kAddPW + (ax0 - px0)) * ps; s11 = pb + (uint32_t)((ay1 - py0) * kAddPW + (ax1 - px0)) * ps;
+        } else {
+          const float* ab = L.add_src + (size_t)img * L.add_img;
+          a00 = ab + ((size_t)ay0 * L.add_W + ax0) * L.add_cs; a01 = ab + ((size_t)ay0 * L.add_W + ax1) * L.add_cs;
+          a10 = ab + ((size_t)ay1 * L.add_W + ax0) * L.add_cs; a11 = ab + ((size_t)ay1 * L.add_W + ax1) * L.add_cs;
+        }
       }
+      if (L.add_pbytes) mbar_wait(full_p(acc), (tc_ >> 1) & 1);
       const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (L.fold ? 6 : 2) * ntile);
       // the accumulator buffer goes back to the MMA warps as soon as it has been READ (not after the stores):
       // with only two buffers the MMAs of tile i+2 otherwise wait for the whole epilogue of tile i
@@ -456,6 +491,20 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
         if (lane == 0) mbar_arrive(tmem_empty(acc));
       };
       auto finish16 = [&](float (&v)[16], const int n) {     // v = conv + bias of channels [n, n + 16)
+        if (s00) {
+          // four products per channel (the weights are per pixel): the interpolation costs 4 FMAs instead of 3 lerps
+          const float w00 = (1.f - aly) * (1.f - alx), w01 = (1.f - aly) * alx, w10 = aly * (1.f - alx), w11 = aly * alx;
+          const uint32_t co = (uint32_t)(n - n0) * 4u;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 p = lds_f4(s00 + co + 16u * i), q4 = lds_f4(s01 + co + 16u * i);
+            const float4 r4 = lds_f4(s10 + co + 16u * i), s4 = lds_f4(s11 + co + 16u * i);
+            v[4 * i + 0] += fmaf(w00, p.x, fmaf(w01, q4.x, fmaf(w10, r4.x, w11 * s4.x)));
+            v[4 * i + 1] += fmaf(w00, p.y, fmaf(w01, q4.y, fmaf(w10, r4.y, w11 * s4.y)));
+            v[4 * i + 2] += fmaf(w00, p.z, fmaf(w01, q4.z, fmaf(w10, r4.z, w11 * s4.z)));
+            v[4 * i + 3] += fmaf(w00, p.w, fmaf(w01, q4.w, fmaf(w10, r4.w, w11 * s4.w)));
+          }
+        }
         if (a00) {
           const float ahy = 1.f - aly, ahx = 1.f - alx;
 #pragma unroll
@@ -511,7 +560,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
         st_global_256(L.out_hi + pix + n, h[0], h[1]);
         st_global_256(L.out_lo + pix + n, l[0], l[1]);
       };
-      if (L.fold) {
+      if (THREADS <= 224 && L.fold) {
         // six 16-column pieces per 16 output channels: (hi, lo) parts of the dx = 0, 1, 2 blocks.  Output column x takes
         // block 0 from input column x - 1 (one lane down), block 1 from x, block 2 from x + 1 (one lane up); the 16
         // lanes of an accumulator row are one row of the tile, and lanes 0 / 15 of a row store nothing.
@@ -541,7 +590,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
           }
           finish16(v, n0 + g * 16);
         }
-      } else if (ntile <= 32) {
+      } else if (THREADS <= 224 && ntile <= 32) {
         // whole accumulator row in registers (2 or 4 loads in flight), buffer released, then the math and the stores
         uint32_t r0[16], r1[16], r2[16], r3[16];
         const bool two = ntile == 32 && n0 + 16 < L.cout_store;
@@ -566,17 +615,39 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloLa
       } else {
         int ngroups = 0;
         for (int c = 0; c < ntile && n0 + c < L.cout_store; c += 16) ++ngroups;
-        for (int g = 0; g < ngroups; ++g) {
-          const int c = g * 16, n = n0 + c;
-          float v[16], v2[16];
-          tmem_ld16(trow + (uint32_t)c, v);
-          tmem_ld16(trow + (uint32_t)(ntile + c), v2);
-          if (g == ngroups - 1) release();
+        const int gstep = L.epi8 ? 2 : 1;
+        int last = -1;                                  // this warp's last group
+        for (int g = team; g < ngroups; g += gstep) last = g;
+        // two 16-channel groups per round: four TMEM loads in flight, one wait, and the accumulator buffer goes back
+        // to the MMA warps right after this warp's last read
+        for (int g = team; g < ngroups; g += 2 * gstep) {
+          const int g2 = g + gstep;
+          const bool has2 = g2 < ngroups;
+          uint32_t r0[16], r1[16], r2[16], r3[16];
+          tmem_ld16_nowait(trow + (uint32_t)(g * 16), r0);
+          tmem_ld16_nowait(trow + (uint32_t)(ntile + g * 16), r1);
+          if (has2) {
+            tmem_ld16_nowait(trow + (uint32_t)(g2 * 16), r2);
+            tmem_ld16_nowait(trow + (uint32_t)(ntile + g2 * 16), r3);
+          }
+          tmem_ld_wait16(r0); tmem_ld_wait16(r1);
+          if (has2) { tmem_ld_wait16(r2); tmem_ld_wait16(r3); }
+          if (g == last || (has2 && g2 == last)) release();
+          float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = (v[i] + v2[i]) + __ldg(L.bias + n + i);
-          finish16(v, n);
+          for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + __ldg(L.bias + n0 + g * 16 + i);
+          finish16(v, n0 + g * 16);
+          if (has2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + __ldg(L.bias + n0 + g2 * 16 + i);
+            finish16(v, n0 + g2 * 16);
+          }
         }
-        if (ngroups == 0) release();
+        if (last < 0) release();
+      }
+      if (L.add_pbytes) {                       // the patch buffer goes back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_p(acc));
       }
       if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[6] = clock64();
     }
@@ -626,6 +697,22 @@ int halo_encode_act_map(CUtensorMap* out, const void* base, int c, int cstride, 
   return 0;
 }
 
+// fp32 NHWC tensor the epilogue interpolates from (fused TransitionUp): box = (ntile + 4) channels x kAddPW x kAddPH
+int halo_encode_add_map(CUtensorMap* out, const void* base, int cstride, int W, int H, int N, size_t img_stride_elems,
+                        int ntile) {
+  EncodeTiledFn enc = get_encode2();
+  PF_REQUIRE(enc, PF_ESTATE, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)cstride, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)cstride * 4, (cuuint64_t)W * cstride * 4, (cuuint64_t)img_stride_elems * 4};
+  cuuint32_t box[4] = {(cuuint32_t)(ntile + 4), (cuuint32_t)kAddPW, (cuuint32_t)kAddPH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PF_REQUIRE(r == CUDA_SUCCESS, PF_EINVAL, "cuTensorMapEncodeTiled(additive-term patch, ntile=%d) failed: %d", ntile, (int)r);
+  return 0;
+}
+
 int halo_encode_weight_map(CUtensorMap* out, const void* base, int ktot, int nrows, int ntile, int w) {
   EncodeTiledFn enc = get_encode2();
   PF_REQUIRE(enc, PF_ESTATE, "cuTensorMapEncodeTiled not available from the driver");
@@ -644,7 +731,8 @@ int halo_chunk_width(int cpad) { return cpad >= 64 ? 64 : (cpad >= 32 ? 32 : 16)
 
 // Fills the shared-memory plan of a layer; returns false when it cannot run on this kernel.
 bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
-  const size_t budget = 218 * 1024;
+  const size_t patches = 2 * (size_t)L->add_pbytes;             // fused TransitionUp: two staged low-resolution patches
+  const size_t budget = 218 * 1024 - patches;
   int wmax = 16;
   size_t w_total = 0, w_tx = 0;
   if (L->taps == 9 && L->tap_mask != 0x1FF && L->tap_mask != 0x1B) return false;   // the issue loops know 3x3 and the 2x2 s2d form
@@ -681,7 +769,7 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
     const int cap = 2 * a_tile <= 12 * 1024 ? kMaxA : 4;
     L->stages_a = sa > cap ? cap : sa;
     L->stages_b = 1;
-    *smem_bytes = w_total + (size_t)L->stages_a * 2 * a_tile + 1024;
+    *smem_bytes = w_total + (size_t)L->stages_a * 2 * a_tile + patches + 1024;
     return true;
   }
   if (L->fold) return false;          // the folded form needs resident weights: the caller retries unfolded
@@ -693,7 +781,7 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
   int sb = (int)(rest / b_tile);
   if (sb < 2) return false;
   L->stages_b = sb > kMaxB ? kMaxB : sb;
-  *smem_bytes = (size_t)L->stages_a * 2 * a_tile + (size_t)L->stages_b * b_tile + 1024;
+  *smem_bytes = (size_t)L->stages_a * 2 * a_tile + (size_t)L->stages_b * b_tile + patches + 1024;
   return true;
 }
 
@@ -705,7 +793,8 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
     PF_CHECK_CUDA(cudaGetDevice(&dev));
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       attr_done.fetch_or(bit, std::memory_order_release);
     }
   }
@@ -717,7 +806,7 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   if (use_pdl < 0) { const char* e = getenv("PF_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, nblocks);
-  cfg.blockDim = dim3(kHaloThreads);
+  cfg.blockDim = dim3(L.epi8 ? kHaloThreads8 : kHaloThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr_pdl[1];
@@ -725,7 +814,8 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr_pdl;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel, L, maps_dev));
+  if (L.epi8) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8>, L, maps_dev));
+  else PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads>, L, maps_dev));
   return 0;
 }
 

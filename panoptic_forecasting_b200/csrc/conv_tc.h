@@ -29,6 +29,7 @@ struct TcLayer {
 };
 
 constexpr int kHaloMaxChunks = 32;
+constexpr int kAddPH = 10, kAddPW = 6;   // 16 rows x 8 columns at <= 1/2 scale (align_corners): 8.5 x 4.5 source pixels + 1
 
 // 3x3 / stride-1 layers on the persistent halo kernel (conv_halo.cu)
 struct HaloLayer {
@@ -49,6 +50,7 @@ struct HaloLayer {
   int resident;             // weights stay in shared memory for the whole kernel
   int amax_ncls;            // > 0 (fp32 head only): channel 15 of every stored pixel carries argmax over the first amax_ncls channels (int bits)
   int pool;                 // 2x2 average pool fused into the epilogue: out_* address the pooled tensor (Hout/2 x Wout/2)
+  int epi8;                 // ntile >= 64, not folded: eight epilogue warps (two per TMEM lane quarter, alternate 16-channel groups)
   int fold;                 // 3x3, ntile <= 32, resident: the three taps of a filter row folded into N (10 x 16 box, 8 x 14 output tiles)
   uint32_t w_bytes_total, w_tx_total;
   int cout_store, relu;
@@ -63,6 +65,11 @@ struct HaloLayer {
   int add_H, add_W, add_cs;
   size_t add_img;
   float add_sh, add_sw;
+  // ... staged per tile by TMA into shared memory (add_pbytes > 0): the low-resolution patch a 16 x 8 output tile
+  // interpolates from is kAddPH x kAddPW pixels x (ntile + 4) floats (4 floats of padding per pixel keep the
+  // epilogue's 128-bit reads of neighbouring patch pixels off the same banks); two buffers, like the accumulators
+  int add_map;              // tensor map of add_src: fp32 (C, W, H, N), box (ntile + 4, kAddPW, kAddPH, 1)
+  uint32_t add_pbytes;      // bytes of one patch buffer (1024-aligned); 0 = per-pixel global gathers
   long long* dbg_ts;        // optional: CTA 0 writes phase timestamps (clock64) here
   int dbg_mode;             // timing experiments only (results invalid): 1 = no activation TMA after the first ring pass, 2 = no stores
 };
@@ -71,6 +78,8 @@ int halo_chunk_width(int cpad);
 int halo_encode_act_map(CUtensorMap* out, const void* base, int c, int cstride, int W, int H, int N,
                         size_t img_stride_elems, int w, int hx, int hy);
 int halo_encode_weight_map(CUtensorMap* out, const void* base, int ktot, int nrows, int ntile, int w);
+int halo_encode_add_map(CUtensorMap* out, const void* base, int cstride, int W, int H, int N, size_t img_stride_elems,
+                        int ntile);
 bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes);
 int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblocks, size_t smem_bytes, cudaStream_t st);
 

@@ -92,16 +92,25 @@ def test_every_conv_layer_tcgen05_per_tap_kernel(pf_lib, bg_shapes, monkeypatch)
     layer_sweep(pf_lib, bg_shapes, 1e-4)
 
 
-def test_fused_conv1x1_up_path(pf_lib, bg_shapes, monkeypatch):
-    """PF_TC_FUSE_UP=1: conv1x1_up commuted with the bilinear TransitionUp (low-res 1x1 + gather epilogue)."""
+@pytest.mark.parametrize("gather", ["0", "1"])
+@pytest.mark.parametrize("b,h,w", [(1, 128, 256), (3, 192, 320), (2, 256, 512)])
+def test_fused_conv1x1_up_path(pf_lib, bg_shapes, monkeypatch, gather, b, h, w):
+    """PF_TC_FUSE_UP=1: conv1x1_up commuted with the bilinear TransitionUp -- a low-resolution 1x1 over the upsampled
+    slices into an fp32 buffer, then the high-resolution 1x1 over the skip slices adds its interpolation in the epilogue,
+    from a low-resolution patch staged per tile by TMA (default) or by per-pixel global gathers (PF_TC_FUSE_UP_GATHER=1).
+    No upsampled tensor is written."""
     monkeypatch.setenv("PF_TC_FUSE_UP", "1")
+    monkeypatch.setenv("PF_TC_FUSE_UP_GATHER", gather)
     sd = synthetic.make_bg_state_dict(bg_shapes, seed=7)
-    pc = synthetic.make_pc_inputs(1, 3, 128, 256, "R", seed=7)
+    pc = synthetic.make_pc_inputs(b, 3, h, w, "R", seed=7)
     inp = {"seg": pc["seg"].long(), "depth": pc["depth"].clamp(0.1, 200), "depth_mask": pc["depth_mask"]}
     ref = bg_oracle.predict(sd, inp, None)
     out = gpu_model(sd, None, precision="tc").predict({k: v.cuda() for k, v in inp.items()}, {})
     scale = ref["logits"].abs().max().item()
     assert (out["logits"].cpu() - ref["logits"]).abs().max().item() <= 3e-4 * scale
+    monkeypatch.setenv("PF_TC_FUSE_UP", "0")
+    plain = gpu_model(sd, None, precision="tc").predict({k: v.cuda() for k, v in inp.items()}, {})
+    assert (out["logits"] - plain["logits"]).abs().max().item() <= 3e-4 * scale
 
 
 def test_label_only_fast_path_matches_interpolated_argmax(pf_lib, bg_shapes, monkeypatch):
