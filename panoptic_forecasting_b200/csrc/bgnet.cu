@@ -1222,8 +1222,9 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   }
   *nblocks = nb;
   {
-    const char* e8 = getenv("PF_HALO_EPI8");               // A/B: second epilogue team for the wide-N layers
-    L->epi8 = (!L->fold && L->ntile >= 64 && !(e8 && e8[0] == '0')) ? 1 : 0;
+    const char* e8 = getenv("PF_HALO_EPI8");               // A/B: second epilogue team (0 = off, n = minimum N tile)
+    const int e8min = e8 && e8[0] ? atoi(e8) : 32;
+    L->epi8 = (!L->fold && e8min > 0 && L->ntile >= e8min && L->ntile >= 32) ? 1 : 0;
   }
   L->Hout = io.Hout; L->Wout = io.Wout; L->batch = io.b;
   L->tiles_x = cdiv(io.Wout, 8); L->tiles_y = cdiv(io.Hout, 16);

@@ -45,6 +45,15 @@ __device__ __forceinline__ uint32_t align1k(uint32_t x) { return (x + 1023u) & ~
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// t / d for 0 <= t < 2^24 (tile indices) with a precomputed float reciprocal: one multiply, one conversion, one fix-up
+// (a 32-bit integer division by a run-time divisor is ~20 instructions, and every epilogue thread did two per tile)
+__device__ __forceinline__ int fast_div(int t, int d, float inv_d) {
+  int q = __float2int_rz((float)t * inv_d);
+  const int r = t - q * d;
+  q += (r >= d) ? 1 : 0;
+  q -= (r < 0) ? 1 : 0;
+  return q;
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -273,6 +282,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
   const int n0 = blockIdx.y * ntile;
   const int tiles_per_img = L.tiles_x * L.tiles_y;
   const int total_tiles = tiles_per_img * L.batch;
+  const float inv_tpi = 1.0f / (float)tiles_per_img, inv_tx = 1.0f / (float)L.tiles_x;
   const int HX = L.hx, HY = L.hy, NT = L.taps;     // 3x3: 10 x 18 box, 9 taps; 1x1: 8 x 16 box, 1 tap
   const int org = NT == 9 ? 1 : 0;                  // box origin = tile origin - pad
 
@@ -340,9 +350,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       long long wait_acc = 0;
       const int nchunk = L.nchunk;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int img = t / tiles_per_img;
+        const int img = fast_div(t, tiles_per_img, inv_tpi);
         const int r = t - img * tiles_per_img;
-        const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
+        const int ty = fast_div(r, L.tiles_x, inv_tx), tx = r - ty * L.tiles_x;
         const int y0 = L.fold ? ty * 8 : ty * 16, x0 = L.fold ? tx * 14 : tx * 8;
         if (L.add_pbytes) {
           // the low-resolution patch this tile's epilogue interpolates from (origin = source pixel of the tile's first
@@ -439,11 +449,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
     for (int g = 0; g < 2; ++g)
 #pragma unroll
       for (int i = 0; i < 16; ++i) bias_r[g][i] = (ntile <= 32 && g * 16 < ntile && n0 + g * 16 < L.cout_store) ? __ldg(L.bias + n0 + g * 16 + i) : 0.f;
+    // wide path (ntile > 32): the bias of this warp's first two 16-channel groups (all it has when ntile <= 64 with two
+    // teams, or <= 32 with one)
+    float bias_w[2][16];
+    {
+      const int gs = (THREADS > 224 && L.epi8) ? 2 : 1;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int ch = n0 + (team + k * gs) * 16 + i;
+          bias_w[k][i] = (THREADS > 224 && (team + k * gs) * 16 < ntile && ch < L.cout_store) ? __ldg(L.bias + ch) : 0.f;
+        }
+    }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
       const int acc = tc_ & 1;
-      const int img = t / tiles_per_img;
+      const int img = fast_div(t, tiles_per_img, inv_tpi);
       const int r = t - img * tiles_per_img;
-      const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
+      const int ty = fast_div(r, L.tiles_x, inv_tx), tx = r - ty * L.tiles_x;
       // fold: accumulator row m = input column x' = m & 15 of row m >> 4; output column = x' - 1 + tile origin
       const int oy = L.fold ? ty * 8 + (m >> 4) : ty * 16 + (m >> 3);
       const int ox = L.fold ? tx * 14 + (m & 15) - 1 : tx * 8 + (m & 7);
@@ -618,6 +641,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         const int gstep = L.epi8 ? 2 : 1;
         int last = -1;                                  // this warp's last group
         for (int g = team; g < ngroups; g += gstep) last = g;
+        const bool bias_in_regs = THREADS > 224 && last >= 0 && last <= team + gstep;   // at most two groups: their bias sits in bias_w
         // two 16-channel groups per round: four TMEM loads in flight, one wait, and the accumulator buffer goes back
         // to the MMA warps right after this warp's last read
         for (int g = team; g < ngroups; g += 2 * gstep) {
@@ -635,11 +659,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           if (g == last || (has2 && g2 == last)) release();
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + __ldg(L.bias + n0 + g * 16 + i);
+          for (int i = 0; i < 16; ++i)
+            v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + (bias_in_regs ? bias_w[0][i] : __ldg(L.bias + n0 + g * 16 + i));
           finish16(v, n0 + g * 16);
           if (has2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + __ldg(L.bias + n0 + g2 * 16 + i);
+            for (int i = 0; i < 16; ++i)
+              v[i] = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + (bias_in_regs ? bias_w[1][i] : __ldg(L.bias + n0 + g2 * 16 + i));
             finish16(v, n0 + g2 * 16);
           }
         }

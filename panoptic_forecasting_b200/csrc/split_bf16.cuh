@@ -14,13 +14,6 @@ __device__ __forceinline__ void split1(float x, unsigned* hi, unsigned* lo) {
   *lo = (unsigned)__bfloat16_as_ushort(l);
 }
 
-__device__ __forceinline__ void split_store4(const float4& r, uint2* h, uint2* l) {
-  unsigned h0, h1, h2, h3, l0, l1, l2, l3;
-  split1(r.x, &h0, &l0); split1(r.y, &h1, &l1); split1(r.z, &h2, &l2); split1(r.w, &h3, &l3);
-  h->x = h0 | (h1 << 16); h->y = h2 | (h3 << 16);
-  l->x = l0 | (l1 << 16); l->y = l2 | (l3 << 16);
-}
-
 // two values at once: one packed cvt.rn.bf16x2.f32 per plane
 __device__ __forceinline__ void split2(float a, float b, unsigned* hi, unsigned* lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -30,6 +23,16 @@ __device__ __forceinline__ void split2(float a, float b, unsigned* hi, unsigned*
   const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
   *hi = hu;
   *lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
+// four values: packed conversions (F2FP.BF16.F32.PACK_AB, full rate) instead of eight scalar F2F (quarter-rate
+// conversion pipe) -- same roundings, bit-identical planes; every conv epilogue goes through this
+__device__ __forceinline__ void split_store4(const float4& r, uint2* h, uint2* l) {
+  unsigned h01, l01, h23, l23;
+  split2(r.x, r.y, &h01, &l01);
+  split2(r.z, r.w, &h23, &l23);
+  h->x = h01; h->y = h23;
+  l->x = l01; l->y = l23;
 }
 
 __device__ __forceinline__ float bf16lo(unsigned packed) { return __uint_as_float(packed << 16); }
