@@ -51,9 +51,9 @@ const char* pf_last_error(void);
  * mode); the per-frame mode (only_this_ind=i) is the same call with t=1 on frame i's slices.
  * Ties on depth go to the lowest flattened source index e = replica*t*N + frame*N + v*W + u.
  * ------------------------------------------------------------------------------------- */
-/* Work space: the z-buffers (8 bytes per target cell) of ONE group of batch items -- a slab of at most
- * PF_ZSPLAT_L2_MB (default 64) MiB, or one item if that is larger, reused by every group so that it stays in
- * L2 -- plus one bit per output cell.  Sized for the per-frame mode. */
+/* Work space: one z-buffer (8 bytes per target cell) per plane of the call plus one bit per output cell (default
+ * scheme; with PF_ZSPLAT_MODE=slab only the z-buffers of ONE L2-sized group, PF_ZSPLAT_L2_MB MiB, reused by every
+ * group).  Sized for the per-frame mode.  The environment is read per call: query with the one you run with. */
 size_t pf_zsplat_workspace_bytes(int b, int t, int H, int W);
 
 int pf_zsplat_forward(const float* depth_dev, const uint8_t* mask_dev, const uint8_t* seg_dev,
