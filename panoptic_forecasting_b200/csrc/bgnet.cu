@@ -1224,7 +1224,13 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   {
     const char* e8 = getenv("PF_HALO_EPI8");               // A/B: second epilogue team (0 = off, n = minimum N tile)
     const int e8min = e8 && e8[0] ? atoi(e8) : 32;
-    L->epi8 = (!L->fold && e8min > 0 && L->ntile >= e8min && L->ntile >= 32) ? 1 : 0;
+    L->epi8 = (!L->fold && e8min > 0 && L->ntile >= e8min && L->ntile >= 32) ? 2 : 0;       // epilogue teams (0 = one)
+    // four teams (608 threads, one group per round) for N tiles >= 64: base.5 216 -> 185 us, base.8 98 -> 74 us per 16
+    // frames; not for the fused conv1x1_up layers, whose interpolating epilogue got slower (365 -> 381 us).
+    // A/B PF_HALO_EPI16: 0 = never, 1 = also for those.
+    const char* e16 = getenv("PF_HALO_EPI16");
+    const bool never = e16 && e16[0] == '0', always = e16 && e16[0] == '1';
+    if (L->epi8 && L->ntile >= 64 && !never && (always || !L->add_pbytes)) L->epi8 = 4;
   }
   L->Hout = io.Hout; L->Wout = io.Wout; L->batch = io.b;
   L->tiles_x = cdiv(io.Wout, 8); L->tiles_y = cdiv(io.Hout, 16);

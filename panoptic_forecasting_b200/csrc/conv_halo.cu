@@ -34,7 +34,7 @@ using namespace tc;
 
 namespace {
 constexpr int kMaxA = 8, kMaxB = 8;
-constexpr int kHaloThreads = 224, kHaloThreads8 = 352;      // warp 0 TMA producer, warps 1 and 6 MMA issuers, warps 2..5 (+ 7..10: HaloLayer::epi8) epilogue
+constexpr int kHaloThreads = 224, kHaloThreads8 = 352, kHaloThreads16 = 608;   // 1 / 2 / 4 epilogue teams      // warp 0 TMA producer, warps 1 and 6 MMA issuers, warps 2..5 (+ 7..10: HaloLayer::epi8) epilogue
 
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
     for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
     mbar_init(wbar, 1);
     // both MMA warps commit to tmem_full after their last chunk of a tile (a commit only covers the issuing thread's MMAs)
-    const uint32_t nepi = L.epi8 ? 8u : 4u;              // epilogue warps that hand the buffers back
+    const uint32_t nepi = 4u * (uint32_t)(L.epi8 ? L.epi8 : 1);   // epilogue warps that hand the buffers back (epi8 = teams)
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), L.nchunk >= 2 ? 2 : 1); mbar_init(tmem_empty(a), nepi); }
     for (int a = 0; a < 2; ++a) { mbar_init(full_p(a), 1); mbar_init(empty_p(a), nepi); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -437,10 +437,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       }
     }
     __syncwarp();
-  } else if (warp <= 5 || (THREADS > 224 && L.epi8)) {
+  } else if (warp <= 5 || (THREADS > 224 && L.epi8 > 1)) {
     // ===== epilogue =====
     const int q = warp & 3;                    // TMEM lane quarter (warps 7..10 -> 3, 0, 1, 2)
-    const int team = warp >= 7 ? 1 : 0;        // second team: odd 16-channel groups
+    const int team = warp >= 7 ? 1 + ((warp - 7) >> 2) : 0;   // extra teams take the other 16-channel groups (round robin)
     const int m = q * 32 + lane;
     int tc_ = 0;
     long long wait_epi = 0, w0 = 0;
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
     // teams, or <= 32 with one)
     float bias_w[2][16];
     {
-      const int gs = (THREADS > 224 && L.epi8) ? 2 : 1;
+      const int gs = (THREADS > 224 && L.epi8) ? L.epi8 : 1;
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll
@@ -638,15 +638,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       } else {
         int ngroups = 0;
         for (int c = 0; c < ntile && n0 + c < L.cout_store; c += 16) ++ngroups;
-        const int gstep = L.epi8 ? 2 : 1;
+        const int gstep = (THREADS > 224 && L.epi8) ? L.epi8 : 1;
         int last = -1;                                  // this warp's last group
         for (int g = team; g < ngroups; g += gstep) last = g;
         const bool bias_in_regs = THREADS > 224 && last >= 0 && last <= team + gstep;   // at most two groups: their bias sits in bias_w
         // two 16-channel groups per round: four TMEM loads in flight, one wait, and the accumulator buffer goes back
         // to the MMA warps right after this warp's last read
-        for (int g = team; g < ngroups; g += 2 * gstep) {
+        for (int g = team; g < ngroups; g += (THREADS <= 352 ? 2 : 1) * gstep) {
           const int g2 = g + gstep;
-          const bool has2 = g2 < ngroups;
+          const bool has2 = THREADS <= 352 && g2 < ngroups;      // the four-team instantiation (104 registers) takes one group per round
           uint32_t r0[16], r1[16], r2[16], r3[16];
           tmem_ld16_nowait(trow + (uint32_t)(g * 16), r0);
           tmem_ld16_nowait(trow + (uint32_t)(ntile + g * 16), r1);
@@ -821,6 +821,7 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
     if (!(attr_done.load(std::memory_order_acquire) & bit)) {
       PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       attr_done.fetch_or(bit, std::memory_order_release);
     }
   }
@@ -832,7 +833,7 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   if (use_pdl < 0) { const char* e = getenv("PF_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, nblocks);
-  cfg.blockDim = dim3(L.epi8 ? kHaloThreads8 : kHaloThreads);
+  cfg.blockDim = dim3(L.epi8 >= 4 ? kHaloThreads16 : (L.epi8 ? kHaloThreads8 : kHaloThreads));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr_pdl[1];
@@ -840,7 +841,8 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr_pdl;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  if (L.epi8) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8>, L, maps_dev));
+  if (L.epi8 >= 4) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads16>, L, maps_dev));
+  else if (L.epi8) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8>, L, maps_dev));
   else PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads>, L, maps_dev));
   return 0;
 }
