@@ -1228,6 +1228,8 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     // four teams (608 threads, one group per round) for N tiles >= 64: base.5 216 -> 185 us, base.8 98 -> 74 us per 16
     // frames; not for the fused conv1x1_up layers, whose interpolating epilogue got slower (365 -> 381 us).
     // A/B PF_HALO_EPI16: 0 = never, 1 = also for those.
+    const char* ft = getenv("PF_HALO_FOLD_TEAMS");         // A/B: two epilogue teams for folded layers with two 16-channel groups
+    if (L->fold && L->ntile == 32 && ft && ft[0] == '1') L->epi8 = 2;
     const char* e16 = getenv("PF_HALO_EPI16");
     const bool never = e16 && e16[0] == '0', always = e16 && e16[0] == '1';
     if (L->epi8 && L->ntile >= 64 && !never && (always || !L->add_pbytes)) L->epi8 = 4;

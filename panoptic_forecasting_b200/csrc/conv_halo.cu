@@ -249,7 +249,8 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
   if (dbg && el) { L.dbg_ts[7] = clock64(); L.dbg_ts[9] = wait_full; L.dbg_ts[10] = wait_tmem; }
 }
 
-template <int THREADS>
+// MODE 0: every epilogue path (one team); 1: wide path only (2 / 4 teams); 2: folded path only, two teams
+template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxB + 9];
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int ch = n0 + (team + k * gs) * 16 + i;
-          bias_w[k][i] = (THREADS > 224 && (team + k * gs) * 16 < ntile && ch < L.cout_store) ? __ldg(L.bias + ch) : 0.f;
+          bias_w[k][i] = (MODE == 1 && (team + k * gs) * 16 < ntile && ch < L.cout_store) ? __ldg(L.bias + ch) : 0.f;
         }
     }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
@@ -583,14 +584,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         st_global_256(L.out_hi + pix + n, h[0], h[1]);
         st_global_256(L.out_lo + pix + n, l[0], l[1]);
       };
-      if (THREADS <= 224 && L.fold) {
+      if (MODE != 1 && L.fold) {
         // six 16-column pieces per 16 output channels: (hi, lo) parts of the dx = 0, 1, 2 blocks.  Output column x takes
         // block 0 from input column x - 1 (one lane down), block 1 from x, block 2 from x + 1 (one lane up); the 16
         // lanes of an accumulator row are one row of the tile, and lanes 0 / 15 of a row store nothing.
         const int ng = (ntile == 32 && n0 + 16 < L.cout_store) ? 2 : 1;
+        if (MODE == 2 && team >= ng) release();           // a team without a group of its own
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g >= ng) break;
+          if (MODE == 2 && g != team) continue;           // two teams: one 16-channel group each
           uint32_t h0[16], h1[16], h2[16], l0[16], l1[16], l2[16];
           const uint32_t c = trow + (uint32_t)(g * 16);
           tmem_ld16_nowait(c, h0);
@@ -601,7 +604,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           tmem_ld16_nowait(c + (uint32_t)(5 * ntile), l2);
           tmem_ld_wait16(h0); tmem_ld_wait16(h1); tmem_ld_wait16(h2);
           tmem_ld_wait16(l0); tmem_ld_wait16(l1); tmem_ld_wait16(l2);
-          if (g == ng - 1) release();
+          if (MODE == 2 || g == ng - 1) release();
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           }
           finish16(v, n0 + g * 16);
         }
-      } else if (THREADS <= 224 && ntile <= 32) {
+      } else if (MODE == 0 && ntile <= 32) {
         // whole accumulator row in registers (2 or 4 loads in flight), buffer released, then the math and the stores
         uint32_t r0[16], r1[16], r2[16], r3[16];
         const bool two = ntile == 32 && n0 + 16 < L.cout_store;
@@ -635,13 +638,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + bias_r[1][i];
           finish16(v, n0 + 16);
         }
-      } else {
+      } else if (MODE != 2) {
         int ngroups = 0;
         for (int c = 0; c < ntile && n0 + c < L.cout_store; c += 16) ++ngroups;
         const int gstep = (THREADS > 224 && L.epi8) ? L.epi8 : 1;
         int last = -1;                                  // this warp's last group
         for (int g = team; g < ngroups; g += gstep) last = g;
-        const bool bias_in_regs = THREADS > 224 && last >= 0 && last <= team + gstep;   // at most two groups: their bias sits in bias_w
+        const bool bias_in_regs = MODE == 1 && last >= 0 && last <= team + gstep;   // at most two groups: their bias sits in bias_w
         // two 16-channel groups per round: four TMEM loads in flight, one wait, and the accumulator buffer goes back
         // to the MMA warps right after this warp's last read
         for (int g = team; g < ngroups; g += (THREADS <= 352 ? 2 : 1) * gstep) {
@@ -819,9 +822,10 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
     PF_CHECK_CUDA(cudaGetDevice(&dev));
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       attr_done.fetch_or(bit, std::memory_order_release);
     }
   }
@@ -841,9 +845,10 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr_pdl;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  if (L.epi8 >= 4) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads16>, L, maps_dev));
-  else if (L.epi8) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8>, L, maps_dev));
-  else PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads>, L, maps_dev));
+  if (L.epi8 >= 4) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads16, 1>, L, maps_dev));
+  else if (L.epi8 && L.fold) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 2>, L, maps_dev));
+  else if (L.epi8) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 1>, L, maps_dev));
+  else PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads, 0>, L, maps_dev));
   return 0;
 }
 
