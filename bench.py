@@ -302,7 +302,8 @@ def parity_block(pipe_fast, bg_fast, host_ref_inputs, dev, precision):
     del full_model, full
     return {"frame": "1 target frame of the benched workload (set 0, item 0) vs oracle/cpu_port.py",
             "pixels": int(mism.numel()), "label_mismatch_px": n,
-            "all_near_ties": bool(gap <= 2.0 * eps + 1e-6 * scale),
+            "all_near_ties": bool(gap <= 2.0 * eps + 1e-6 * scale) and bool(eps <= 1e-3 * scale),
+            "within_tolerance": bool(eps <= 1e-3 * scale) and stage_a,
             "worst_ref_gap_at_mismatch_rel": gap / scale, "logits_rel_err": eps / scale,
             "stage_a_bit_exact": stage_a,
             "near_tie_definition": "reference logit of our class within 2 x (max abs logit error) of the reference maximum"}, t_ref, ref

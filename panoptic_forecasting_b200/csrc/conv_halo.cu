@@ -661,9 +661,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           if (has2) { tmem_ld_wait16(r2); tmem_ld_wait16(r3); }
           if (g == last || (has2 && g2 == last)) release();
           float v[16];
+          // bias_w[0] / [1] = this warp's first / second group; in the one-group-per-round form the second group is the
+          // first slot of the second round
+          const bool second = THREADS > 352 && g != team;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + (bias_in_regs ? bias_w[0][i] : __ldg(L.bias + n0 + g * 16 + i));
+            v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) +
+                   (bias_in_regs ? (second ? bias_w[1][i] : bias_w[0][i]) : __ldg(L.bias + n0 + g * 16 + i));
           finish16(v, n0 + g * 16);
           if (has2) {
 #pragma unroll
