@@ -167,6 +167,15 @@ int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* de
                      float* out_quarter_dev, float* out_full_dev,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* The same forward for the reference's `convert2onehot: False` input mode (bg_model.py:61-65: `inps` already is a
+ * float tensor of per-class planes): scores_dev f32 [b, num_inputs, classes, H, W] replaces labels_dev; everything
+ * else as pf_bgnet_forward.  Only the first ConvLayer differs (dense planes instead of the label look-up). */
+int pf_bgnet_forward_dense(pf_bgnet_t* net, const float* scores_dev, const float* depth_dev,
+                           const uint8_t* mask_dev, int b, int H, int W, int final_h, int final_w,
+                           uint8_t* out_seg_u8_dev, int64_t* out_seg_i64_dev,
+                           float* out_quarter_dev, float* out_full_dev,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* number of kernel launches one pf_bgnet_forward enqueues (for bench.py's gpu_launches) */
 int pf_bgnet_launches_per_forward(const pf_bgnet_t* net);
 int pf_zsplat_launches_per_forward(void);

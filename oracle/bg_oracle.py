@@ -179,3 +179,26 @@ def predict(sd, inputs, final_size=None):
         x = bg_inputs_to_planes(sd, inputs["seg"], inputs["depth"], inputs["depth_mask"])
         logits, quarter = hardnet_forward(sd, x, final_size)
         return {"seg": logits.argmax(1), "logits": logits, "orig_size_logits": quarter}
+
+
+def predict_dense(sd, inputs, final_size=None):
+    """bg_model.py:61-69,91-102 with `convert2onehot` off: inputs['seg'] already is a float [b,t,C,H,W] tensor of
+    per-class planes; it is flattened to [b, t*C, H, W] and the t normalised masked depth planes are appended."""
+    with torch.no_grad():
+        inps = inputs["seg"].float()
+        b, t, c, h, w = inps.shape
+        x = inps.reshape(b, t * c, h, w)
+        dn = (inputs["depth"] - sd["depth_mean"]) / sd["depth_std"]
+        dn = dn * inputs["depth_mask"]
+        logits, quarter = hardnet_forward(sd, torch.cat([x, dn], 1), final_size)
+        return {"seg": logits.argmax(1), "logits": logits, "orig_size_logits": quarter}
+
+
+def loss(sd, inputs, labels, final_size=None, dense=False):
+    """bg_model.py:73-89: cross entropy (ignore_index 255) and pixel accuracy of the full-size logits."""
+    out = (predict_dense if dense else predict)(sd, inputs, final_size)
+    target = labels["seg"].long()
+    ls = F.cross_entropy(out["logits"], target, ignore_index=255)
+    correct = (out["logits"].argmax(1) == target).sum()
+    total = (target != 255).sum()
+    return {"loss": ls, "accuracy": correct.float() / total.float()}

@@ -42,6 +42,7 @@ SIGNATURES = {
     "pf_bgnet_set_depth_norm": (_i, [_vp, _f, _f]),
     "pf_bgnet_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "pf_bgnet_forward": (_i, [_vp] * 4 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
+    "pf_bgnet_forward_dense": (_i, [_vp] * 4 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
     "pf_bgnet_launches_per_forward": (_i, [_vp]),
     "pf_bgnet_set_profiling": (_i, [_vp, _i]),
     "pf_bgnet_num_steps": (_i, [_vp]),

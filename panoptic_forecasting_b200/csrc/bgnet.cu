@@ -503,6 +503,88 @@ __global__ void __launch_bounds__(F_TH* F_TW) first_conv_kernel(const __grid_con
   }
 }
 
+// First ConvLayer from DENSE per-class planes: the reference's `convert2onehot: False` input mode (bg_model.py:61-69,
+// `inps` is already a float [b, t, C, H, W] tensor of class scores / one-hot planes).  Same weight tables as the label
+// form: lut[tap][frame][class] is the folded weight row of input channel frame * C + class, wd the depth planes'.  One
+// output pixel per thread, 16 accumulators; the planes are read straight from global memory (stride-2 taps: half of
+// every line is used, the other half by the neighbouring tap), the weight rows as broadcast 128-bit shared loads.
+// Not on the benched path (the reference's bg configs all use one-hot conversion): written for coverage, not for speed.
+struct FirstDenseParams {
+  const float* x;        // [b, t, C, H, W]
+  const float* depth;    // [b, t, H, W] or null
+  const uint8_t* mask;   // [b, t, H, W] or null
+  const float* tab;      // lut | wd | bias (| lutsum, unused here)
+  void* out;
+  void* out_lo;
+  int split;
+  int b, t, H, W, Ho, Wo, ncls, use_depth;
+  float mean, std;
+};
+
+__global__ void __launch_bounds__(F_TH* F_TW) first_conv_dense_kernel(const FirstDenseParams p) {
+  extern __shared__ __align__(16) float dtab[];
+  const int lut_floats = 9 * p.t * (p.ncls + 1) * 16, wd_floats = 9 * p.t * 16;
+  for (int i = threadIdx.x; i < lut_floats + wd_floats + 16; i += blockDim.x) dtab[i] = __ldg(p.tab + i);
+  __syncthreads();
+  const float* lut = dtab;
+  const float* wd = dtab + lut_floats;
+  const float* bias = wd + wd_floats;
+  const int px = threadIdx.x % F_TW, py = threadIdx.x / F_TW;
+  const int ox = blockIdx.x * F_TW + px, oy = blockIdx.y * F_TH + py, img = blockIdx.z;
+  if (ox >= p.Wo || oy >= p.Ho) return;
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = bias[o];
+  const size_t plane = (size_t)p.H * p.W;
+  int off[9];
+  bool in[9];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int iy = 2 * oy + dy - 1, ix = 2 * ox + dx - 1;
+      in[dy * 3 + dx] = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      off[dy * 3 + dx] = iy * p.W + ix;
+    }
+  auto add_plane = [&](const float* src, const float* wrow0, int wstride, bool is_depth, const uint8_t* msk) {
+    float v[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      float x = in[tap] ? __ldg(src + off[tap]) : 0.f;
+      if (is_depth && in[tap]) {
+        // bg_model.py:50-51,67-68: (depth - mean) / std, then * depth_mask
+        const float n = __fdiv_rn(__fadd_rn(x, -p.mean), p.std);
+        x = __ldg(msk + off[tap]) ? n : __fmul_rn(n, 0.0f);
+      }
+      v[tap] = x;
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float4* row = reinterpret_cast<const float4*>(wrow0 + (size_t)tap * wstride);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = row[q];
+        acc[4 * q + 0] = fmaf(v[tap], w.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(v[tap], w.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v[tap], w.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v[tap], w.w, acc[4 * q + 3]);
+      }
+    }
+  };
+  for (int f = 0; f < p.t; ++f) {
+    for (int cls = 0; cls < p.ncls; ++cls)
+      add_plane(p.x + ((size_t)(img * p.t + f) * p.ncls + cls) * plane, lut + ((size_t)f * (p.ncls + 1) + cls) * 16,
+                p.t * (p.ncls + 1) * 16, false, nullptr);
+    if (p.use_depth)
+      add_plane(p.depth + (size_t)(img * p.t + f) * plane, wd + (size_t)f * 16, p.t * 16, true,
+                p.mask + (size_t)(img * p.t + f) * plane);
+  }
+  float v[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) v[o] = fmaxf(acc[o], 0.f);
+  store16_any(p.out, p.out_lo, (((size_t)img * p.Ho + oy) * p.Wo + ox) * 16, v, p.split != 0);
+}
+
 // tensor maps of the caller's input tensors for first_conv_kernel (encoded per call: pointers are the caller's)
 static int first_conv_maps(FirstMaps* p, const uint8_t* labels, const float* depth, const uint8_t* mask, int bt, int H,
                            int W, bool use_depth) {
@@ -1233,6 +1315,22 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     const char* e16 = getenv("PF_HALO_EPI16");
     const bool never = e16 && e16[0] == '0', always = e16 && e16[0] == '1';
     if (L->epi8 && L->ntile >= 64 && !never && (always || !L->add_pbytes)) L->epi8 = 4;
+    // alternate-tile epilogue teams (conv_halo_kernel<352, 3>: team k owns accumulator buffer k) for N tiles <= 32.
+    // Measured per 16 frames: base.1 (16->24 at 1/2 resolution, one 16-channel chunk = 18 MMAs per tile, the epilogue
+    // is the whole cost) 500 -> 449 us against two column teams; no gain anywhere else -- the one-team K-light layers
+    // (18->10: 113 us either way) are bound by the MMAs' shared-memory A fetch, the folded ones by the tensor pipe --
+    // and the N = 32 layers with more K (base.2, 30->18) lose 2-8 %.  Default: only the single-16-channel-chunk case.
+    // A/B PF_HALO_ALT: bit 0 = unfolded layers with one team, bit 1 = folded layers, bit 2 = every N = 32 unfolded
+    // layer that otherwise runs two column teams; 0 = never.
+    const char* al = getenv("PF_HALO_ALT");
+    const bool alt_auto = !(al && al[0]);
+    const int alt = alt_auto ? 0 : atoi(al);
+    if (L->ntile <= 32 && !L->add_pbytes && !L->add_src) {
+      if (!L->fold && !L->epi8 && (alt & 1)) L->alt = 1;
+      if (L->fold && !L->epi8 && (alt & 2)) L->alt = 1;
+      const bool one_small_chunk = L->nchunk == 1 && L->seg_cpad[0] == 16;
+      if (!L->fold && L->epi8 == 2 && ((alt & 4) || (alt_auto && one_small_chunk))) { L->alt = 1; L->epi8 = 0; }
+    }
   }
   L->Hout = io.Hout; L->Wout = io.Wout; L->batch = io.b;
   L->tiles_x = cdiv(io.Wout, 8); L->tiles_y = cdiv(io.Hout, 16);
@@ -1559,11 +1657,12 @@ static int run_conv(pf_bgnet* net, const Arena& a, int ci, cudaStream_t st) {
   return launch_conv_simt(L, c.ksize, c.exec_stride(), sp, sp && !head, st);
 }
 
-extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* depth_dev,
-                                const uint8_t* mask_dev, int b, int H, int W, int final_h, int final_w,
-                                uint8_t* out_seg_u8_dev, int64_t* out_seg_i64_dev, float* out_quarter_dev,
-                                float* out_full_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
-  PF_REQUIRE(net && labels_dev && workspace_dev, PF_EINVAL, "pf_bgnet_forward: null pointer");
+// labels_dev (uint8 class ids, the one-hot conversion is implicit) or scores_dev (dense per-class planes): exactly one
+static int bgnet_forward_impl(pf_bgnet_t* net, const uint8_t* labels_dev, const float* scores_dev, const float* depth_dev,
+                              const uint8_t* mask_dev, int b, int H, int W, int final_h, int final_w,
+                              uint8_t* out_seg_u8_dev, int64_t* out_seg_i64_dev, float* out_quarter_dev,
+                              float* out_full_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  PF_REQUIRE(net && (labels_dev || scores_dev) && workspace_dev, PF_EINVAL, "pf_bgnet_forward: null pointer");
   PF_REQUIRE(!net->use_depth || (depth_dev && mask_dev), PF_EINVAL, "pf_bgnet_forward: depth inputs required");
   PF_REQUIRE(b > 0 && H > 0 && W > 0 && H % 64 == 0 && W % 64 == 0, PF_EINVAL,
              "pf_bgnet_forward: H and W must be positive multiples of 64 (got %dx%d)", H, W);
@@ -1590,6 +1689,19 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
     switch (s.type) {
       case STEP_FIRST: {
         const ConvDesc& c = net->convs[s.conv];
+        if (scores_dev) {
+          FirstDenseParams d;
+          d.x = scores_dev; d.depth = depth_dev; d.mask = mask_dev; d.tab = net->first_tab_dev;
+          d.out = a.ptr(c.out.buf, 0); d.out_lo = a.ptr_lo(c.out.buf, 0); d.split = split;
+          d.b = b; d.t = net->num_inputs; d.H = H; d.W = W; d.Ho = H / 2; d.Wo = W / 2;
+          d.ncls = net->num_classes; d.use_depth = net->use_depth; d.mean = net->depth_mean; d.std = net->depth_std;
+          const size_t dsm = ((size_t)9 * d.t * (d.ncls + 1) * 16 + (size_t)9 * d.t * 16 + 16) * sizeof(float);
+          PF_REQUIRE(dsm <= 160 * 1024, PF_EINVAL, "pf_bgnet_forward_dense: first-conv tables too large");
+          PF_CHECK_CUDA(cudaFuncSetAttribute(first_conv_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          first_conv_dense_kernel<<<dim3(cdiv(d.Wo, F_TW), cdiv(d.Ho, F_TH), b), F_TH * F_TW, dsm, st>>>(d);
+          PF_CHECK_CUDA(cudaGetLastError());
+          break;
+        }
         FirstParams p;
         {
           PF_REQUIRE(((size_t)labels_dev & 15) == 0 && ((size_t)depth_dev & 15) == 0 && ((size_t)mask_dev & 15) == 0,
@@ -1706,6 +1818,24 @@ extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, cons
     net->prof_iter++;
   }
   return 0;
+}
+
+extern "C" int pf_bgnet_forward(pf_bgnet_t* net, const uint8_t* labels_dev, const float* depth_dev,
+                                const uint8_t* mask_dev, int b, int H, int W, int final_h, int final_w,
+                                uint8_t* out_seg_u8_dev, int64_t* out_seg_i64_dev, float* out_quarter_dev,
+                                float* out_full_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  PF_REQUIRE(labels_dev, PF_EINVAL, "pf_bgnet_forward: null pointer");
+  return bgnet_forward_impl(net, labels_dev, nullptr, depth_dev, mask_dev, b, H, W, final_h, final_w, out_seg_u8_dev,
+                            out_seg_i64_dev, out_quarter_dev, out_full_dev, workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int pf_bgnet_forward_dense(pf_bgnet_t* net, const float* scores_dev, const float* depth_dev,
+                                      const uint8_t* mask_dev, int b, int H, int W, int final_h, int final_w,
+                                      uint8_t* out_seg_u8_dev, int64_t* out_seg_i64_dev, float* out_quarter_dev,
+                                      float* out_full_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  PF_REQUIRE(scores_dev, PF_EINVAL, "pf_bgnet_forward_dense: null pointer");
+  return bgnet_forward_impl(net, nullptr, scores_dev, depth_dev, mask_dev, b, H, W, final_h, final_w, out_seg_u8_dev,
+                            out_seg_i64_dev, out_quarter_dev, out_full_dev, workspace_dev, workspace_bytes, stream);
 }
 
 extern "C" int pf_bgnet_set_profiling(pf_bgnet_t* net, int max_iters) {

@@ -249,7 +249,9 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
   if (dbg && el) { L.dbg_ts[7] = clock64(); L.dbg_ts[9] = wait_full; L.dbg_ts[10] = wait_tmem; }
 }
 
-// MODE 0: every epilogue path (one team); 1: wide path only (2 / 4 teams); 2: folded path only, two teams
+// MODE 0: every epilogue path (one team); 1: wide path only (2 / 4 teams); 2: folded path only, two teams;
+// 3: the N <= 32 paths (folded / whole row in registers) with two teams that take ALTERNATE TILES (HaloLayer::alt): team k
+// owns accumulator buffer k, so the epilogue of tile i + 1 runs next to that of tile i instead of behind it
 template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
   extern __shared__ uint8_t smem_raw[];
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
     for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
     mbar_init(wbar, 1);
     // both MMA warps commit to tmem_full after their last chunk of a tile (a commit only covers the issuing thread's MMAs)
-    const uint32_t nepi = 4u * (uint32_t)(L.epi8 ? L.epi8 : 1);   // epilogue warps that hand the buffers back (epi8 = teams)
+    const uint32_t nepi = MODE == 3 ? 4u : 4u * (uint32_t)(L.epi8 ? L.epi8 : 1);   // epilogue warps that hand a buffer back (epi8 = teams)
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), L.nchunk >= 2 ? 2 : 1); mbar_init(tmem_empty(a), nepi); }
     for (int a = 0; a < 2; ++a) { mbar_init(full_p(a), 1); mbar_init(empty_p(a), nepi); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       }
     }
     __syncwarp();
-  } else if (warp <= 5 || (THREADS > 224 && L.epi8 > 1)) {
+  } else if (warp <= 5 || (THREADS > 224 && (MODE == 3 || L.epi8 > 1))) {
     // ===== epilogue =====
     const int q = warp & 3;                    // TMEM lane quarter (warps 7..10 -> 3, 0, 1, 2)
     const int team = warp >= 7 ? 1 + ((warp - 7) >> 2) : 0;   // extra teams take the other 16-channel groups (round robin)
@@ -465,6 +467,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
     }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
       const int acc = tc_ & 1;
+      if (MODE == 3 && acc != team) continue;      // alternate-tile teams: the other team's tile (and accumulator buffer)
       const int img = fast_div(t, tiles_per_img, inv_tpi);
       const int r = t - img * tiles_per_img;
       const int ty = fast_div(r, L.tiles_x, inv_tx), tx = r - ty * L.tiles_x;
@@ -616,7 +619,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           }
           finish16(v, n0 + g * 16);
         }
-      } else if (MODE == 0 && ntile <= 32) {
+      } else if ((MODE == 0 || MODE == 3) && ntile <= 32) {
         // whole accumulator row in registers (2 or 4 loads in flight), buffer released, then the math and the stores
         uint32_t r0[16], r1[16], r2[16], r3[16];
         const bool two = ntile == 32 && n0 + 16 < L.cout_store;
@@ -638,7 +641,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + bias_r[1][i];
           finish16(v, n0 + 16);
         }
-      } else if (MODE != 2) {
+      } else if (MODE <= 1) {
         int ngroups = 0;
         for (int c = 0; c < ntile && n0 + c < L.cout_store; c += 16) ++ngroups;
         const int gstep = (THREADS > 224 && L.epi8) ? L.epi8 : 1;
@@ -830,6 +833,7 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
       PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       attr_done.fetch_or(bit, std::memory_order_release);
     }
   }
@@ -841,7 +845,7 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   if (use_pdl < 0) { const char* e = getenv("PF_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, nblocks);
-  cfg.blockDim = dim3(L.epi8 >= 4 ? kHaloThreads16 : (L.epi8 ? kHaloThreads8 : kHaloThreads));
+  cfg.blockDim = dim3(L.alt ? kHaloThreads8 : L.epi8 >= 4 ? kHaloThreads16 : (L.epi8 ? kHaloThreads8 : kHaloThreads));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr_pdl[1];
@@ -849,7 +853,8 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr_pdl;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  if (L.epi8 >= 4) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads16, 1>, L, maps_dev));
+  if (L.alt) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 3>, L, maps_dev));
+  else if (L.epi8 >= 4) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads16, 1>, L, maps_dev));
   else if (L.epi8 && L.fold) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 2>, L, maps_dev));
   else if (L.epi8) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 1>, L, maps_dev));
   else PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads, 0>, L, maps_dev));

@@ -43,10 +43,9 @@ class BGModel(BaseModel):
         self.num_inputs = params['model'].get('num_inputs', 1)
         self.min_depth = params['data'].get('min_depth')
         self.max_depth = params['data'].get('max_depth')
+        # True: `inps` are class ids (uint8 / int64 [b,t,H,W]); False / None: float per-class planes [b,t,C,H,W]
+        # (bg_model.py:61-65) -- the dense first-conv kernel (pf_bgnet_forward_dense)
         self.convert2onehot = params['model'].get('convert2onehot')
-        if not self.convert2onehot:
-            raise NotImplementedError("the B200 path implements the convert2onehot=True input mode "
-                                      "(the only one the reference's bg configs use)")
         final_w = params['model'].get('final_w')
         final_h = params['model'].get('final_h')
         self.final_size = (final_h, final_w) if final_w is not None and final_h is not None else None
@@ -140,10 +139,19 @@ class BGModel(BaseModel):
             raise NotImplementedError("the B200 path is inference-only (BatchNorm is folded); call .eval()")
         if self._dirty or self._uploaded_device != dev:
             self._upload(dev)
-        b, t, H, W = inps.shape
+        dense = not self.convert2onehot
+        if dense:
+            if inps.dim() != 5 or inps.shape[2] != self.num_classes:
+                raise ValueError("convert2onehot=False expects float planes [b, t, %d, H, W], got %s"
+                                 % (self.num_classes, tuple(inps.shape)))
+            b, t, _, H, W = inps.shape
+        else:
+            b, t, H, W = inps.shape
         if t != self.num_inputs:
             raise ValueError("expected %d input frames, got %d" % (self.num_inputs, t))
-        if inps.dtype == torch.uint8:
+        if dense:
+            labels = inps.to(torch.float32)
+        elif inps.dtype == torch.uint8:
             labels = inps
         else:
             # ids outside [0, 255] (the reference's F.one_hot raises on negatives) take the all-zero one-hot row,
@@ -176,10 +184,11 @@ class BGModel(BaseModel):
             quarter = torch.empty((b, self.num_classes, H // 4, W // 4), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = self._lib.pf_bgnet_forward(self._net, labels.data_ptr(), _lib.ptr(depth_c), _lib.ptr(mask_c),
-                                            b, H, W, fh, fw, _lib.ptr(seg8), _lib.ptr(seg64), _lib.ptr(quarter),
-                                            _lib.ptr(full), self._ws.data_ptr(), self._ws.numel(), stream)
-        _lib.check(rc, "pf_bgnet_forward")
+            fwd = self._lib.pf_bgnet_forward_dense if dense else self._lib.pf_bgnet_forward
+            rc = fwd(self._net, labels.data_ptr(), _lib.ptr(depth_c), _lib.ptr(mask_c),
+                     b, H, W, fh, fw, _lib.ptr(seg8), _lib.ptr(seg64), _lib.ptr(quarter),
+                     _lib.ptr(full), self._ws.data_ptr(), self._ws.numel(), stream)
+        _lib.check(rc, "pf_bgnet_forward_dense" if dense else "pf_bgnet_forward")
         return (seg8 if seg8 is not None else seg64), full, quarter
 
     def forward(self, inps, depths, depth_masks, return_orig_size=False):
@@ -190,8 +199,22 @@ class BGModel(BaseModel):
         return full
 
     def loss(self, inputs, labels):
-        raise NotImplementedError("training is outside the B200 hot path; train with the reference, "
-                                  "then .load() the checkpoint here (same state_dict keys)")
+        """Reference signature (bg_model.py:73-89): cross entropy (ignore_index 255) and pixel accuracy of the
+        full-size logits against labels['seg'].  Evaluation only: the logits come from the inference kernels
+        (BatchNorm folded, no autograd graph), so the returned loss carries no gradient -- this is the number the
+        reference's validation pass logs in .eval() mode; training stays with the reference (same state_dict keys)."""
+        if self.training:
+            raise NotImplementedError("the B200 path is inference-only (BatchNorm is folded): loss() gives the "
+                                      "validation loss / accuracy in .eval() mode; train with the reference, then "
+                                      ".load() the checkpoint here (same state_dict keys)")
+        seg_labels = labels['seg']
+        seg_preds = self(inputs['seg'], inputs.get('depth'), inputs.get('depth_mask'))
+        seg_labels = seg_labels.to(seg_preds.device, torch.int64)
+        seg_loss = nn.functional.cross_entropy(seg_preds, seg_labels, ignore_index=255)
+        max_preds = seg_preds.argmax(1).long()
+        correct = (max_preds == seg_labels).sum()
+        total = (seg_labels != 255).sum()
+        return {'loss': seg_loss, 'accuracy': correct.float() / total.float()}
 
     def predict(self, inputs, labels):
         """Reference signature (bg_model.py:91-102).  'logits' / 'orig_size_logits' are produced

@@ -182,6 +182,24 @@ def make_bg_inputs(b=1, t=3, h=512, w=1024, seed=0, device="cpu", label_dtype=to
     return {"seg": seg.to(dev), "depth": depth.to(dev), "depth_mask": mask.to(dev)}
 
 
+def make_bg_dense_inputs(b=1, t=3, h=64, w=128, seed=0, num_classes=11):
+    """Inputs for BGModel with `convert2onehot` off (bg_model.py:61-65): soft per-class planes [b,t,C,h,w]
+    (softmax of seeded noise), depth / mask as in make_bg_inputs."""
+    base = make_bg_inputs(b, t, h, w, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    scores = torch.softmax(2.0 * torch.randn(b, t, num_classes, h, w, generator=g), dim=2)
+    return {"seg": scores, "depth": base["depth"], "depth_mask": base["depth_mask"]}
+
+
+def make_loss_target(pred_seg, seed=0, num_classes=11):
+    """Label map for BGModel.loss: the predicted map with 30 % of the pixels re-drawn and a band of ignore (255)."""
+    g = torch.Generator().manual_seed(seed + 2000)
+    keep = torch.rand(pred_seg.shape, generator=g) < 0.7
+    target = torch.where(keep, pred_seg.long(), torch.randint(0, num_classes, pred_seg.shape, generator=g))
+    target[:, :5] = 255
+    return target
+
+
 def make_bg_state_dict(ref_state_dict_like, seed=0):
     """Seeded synthetic weights with randomised BatchNorm statistics (so folding is
     exercised). ``ref_state_dict_like``: a state_dict giving names and shapes."""

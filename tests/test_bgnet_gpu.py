@@ -15,7 +15,7 @@ from conftest import bg_params
 from oracle import bg_oracle
 from panoptic_forecasting_b200 import _lib, synthetic
 from panoptic_forecasting_b200.models import build_model
-from test_oracle import golden_bg_inputs
+from test_oracle import golden_bg_inputs, golden_dense_inputs
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -89,6 +89,54 @@ def test_labels_out_of_range_and_masked_depth(pf_lib, bg_shapes):
     ref = bg_oracle.predict(sd, {k: v.clone() for k, v in inp.items()}, None)
     out = gpu_model(sd).predict({k: v.cuda() for k, v in inp.items()}, {})
     check_against(out, ref, rel_tol=1e-4)
+
+
+def test_loss_eval_mode(pf_lib, bg_shapes):
+    """BGModel.loss (bg_model.py:73-89) in .eval() mode against the numbers the unmodified reference produced
+    (tests/golden/loss_iid64.npz) and against the oracle; .train() refuses."""
+    z = np.load(os.path.join(GOLD, "loss_iid64.npz"))
+    sd, inp, target = golden_dense_inputs(z, bg_shapes, dense=False)
+    want = bg_oracle.loss(sd, inp, {"seg": target})
+    for precision in ("fp32", "tc"):
+        m = gpu_model(sd, precision=precision)
+        got = m.loss({k: v.cuda() for k, v in inp.items()}, {"seg": target.cuda()})
+        for ref_loss, ref_acc in ((want["loss"].item(), want["accuracy"].item()), (float(z["loss"]), float(z["accuracy"]))):
+            assert abs(got["loss"].item() - ref_loss) <= 1e-3 * abs(ref_loss), (precision, got["loss"].item(), ref_loss)
+            assert abs(got["accuracy"].item() - ref_acc) <= 1e-3, (precision, got["accuracy"].item(), ref_acc)
+    with pytest.raises(NotImplementedError):
+        m.train().loss({k: v.cuda() for k, v in inp.items()}, {"seg": target.cuda()})
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tc", 3e-4)])
+def test_dense_planes_input_mode(pf_lib, bg_shapes, precision, tol):
+    """`convert2onehot: False` (bg_model.py:61-65): float per-class planes [b,t,C,H,W] through pf_bgnet_forward_dense,
+    against the oracle and the unmodified reference's outputs (tests/golden/dense_soft64.npz).  Soft class scores, so
+    every weight of the first layer matters; one-hot planes must reproduce the label path."""
+    z = np.load(os.path.join(GOLD, "dense_soft64.npz"))
+    sd, dense_in, target = golden_dense_inputs(z, bg_shapes, dense=True)
+    ref = bg_oracle.predict_dense(sd, dense_in, None)
+    p = dict(bg_params(None, None, precision=precision), no_gpu=False)
+    p["model"] = dict(p["model"], convert2onehot=False)
+    md = build_model(p).eval()
+    md.load_state_dict(sd)
+    out = md.predict({k: v.cuda() for k, v in dense_in.items()}, {})
+    check_against(out, ref, rel_tol=tol)
+    scale = np.abs(z["out_quarter"]).max()
+    assert np.abs(out["orig_size_logits"].cpu().numpy() - z["out_quarter"]).max() <= tol * scale
+    assert (out["seg"].cpu().numpy() != z["out_seg"]).mean() <= 1e-3
+    ls = md.loss({k: v.cuda() for k, v in dense_in.items()}, {"seg": target.cuda()})
+    assert abs(ls["loss"].item() - float(z["loss"])) <= 1e-3 * float(z["loss"])
+    # one-hot planes of a label map == the label path of the same net (both accumulate the first layer in fp32; the
+    # summation orders differ)
+    inp = synthetic.make_bg_inputs(2, 3, 64, 128, seed=5)
+    lab = inp["seg"].clamp(max=10)
+    onehot = F.one_hot(lab.long(), 11).permute(0, 1, 4, 2, 3).float()
+    o1 = md.predict({"seg": onehot.cuda(), "depth": inp["depth"].cuda(), "depth_mask": inp["depth_mask"].cuda()}, {})
+    m = gpu_model(sd, precision=precision)
+    o2 = m.predict({"seg": lab.cuda(), "depth": inp["depth"].cuda(), "depth_mask": inp["depth_mask"].cuda()}, {})
+    assert (o1["logits"] - o2["logits"]).abs().max().item() <= tol * o2["logits"].abs().max().item()
+    with pytest.raises(ValueError):
+        md.predict({"seg": lab.cuda(), "depth": inp["depth"].cuda(), "depth_mask": inp["depth_mask"].cuda()}, {})
 
 
 def test_every_conv_layer_vs_torch(pf_lib, bg_shapes):

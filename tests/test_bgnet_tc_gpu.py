@@ -59,11 +59,13 @@ def test_every_conv_layer_tcgen05_many_tiles(pf_lib, bg_shapes, monkeypatch):
     layer_sweep(pf_lib, bg_shapes, 1e-4, hw=(100, 170))
 
 
-@pytest.mark.parametrize("env", [{"PF_HALO_EPI8": "0"}, {"PF_HALO_EPI16": "0"}, {"PF_HALO_EPI16": "1"}, {"PF_HALO_FOLD_TEAMS": "1"}],
+@pytest.mark.parametrize("env", [{"PF_HALO_EPI8": "0"}, {"PF_HALO_EPI16": "0"}, {"PF_HALO_EPI16": "1"}, {"PF_HALO_FOLD_TEAMS": "1"},
+                                 {"PF_HALO_ALT": "7"}, {"PF_HALO_ALT": "0"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_every_conv_layer_tcgen05_epilogue_teams(pf_lib, bg_shapes, monkeypatch, env):
     """The epilogue-team variants of the halo kernel (conv_halo_kernel<224,0> only / two teams everywhere / four teams
-    also for the fused conv1x1_up layers / two teams on the folded layers): same results, enough tiles that every layer
+    also for the fused conv1x1_up layers / two teams on the folded layers / two teams on alternate tiles for every layer
+    with an N tile <= 32 / never): same results, enough tiles that every layer
     keeps its full N tile."""
     monkeypatch.delenv("PF_TC_FORCE_SIMT", raising=False)
     for k, v in env.items():

@@ -54,6 +54,35 @@ def test_bg_oracle_matches_golden(path, bg_shapes):
     assert (out["seg"].numpy() != z["out_seg"]).mean() <= 1e-3
 
 
+def golden_dense_inputs(z, shapes, dense):
+    """inputs of tests/golden/make_golden_dense.py's two cases, regenerated from the stored seed"""
+    h, w, seed = int(z["h"]), int(z["w"]), int(z["seed"])
+    sd = synthetic.make_bg_state_dict(shapes, seed=seed)
+    sd["model.finalConv.bias"] = sd["model.finalConv.bias"] - torch.from_numpy(z["bias_shift"])
+    inp = synthetic.make_bg_dense_inputs(2, 3, h, w, seed=seed) if dense else synthetic.make_bg_inputs(2, 3, h, w, seed=seed)
+    target = synthetic.make_loss_target(torch.from_numpy(z["out_seg"].astype(np.int64)), seed=seed)
+    return sd, inp, target
+
+
+def test_bg_oracle_dense_planes_and_loss_match_golden(bg_shapes):
+    """`convert2onehot` off and BGModel.loss (bg_model.py:61-69,73-89) against the unmodified reference's outputs."""
+    z = np.load(os.path.join(GOLD, "dense_soft64.npz"))
+    sd, inp, target = golden_dense_inputs(z, bg_shapes, dense=True)
+    out = bg_oracle.predict_dense(sd, inp, None)
+    scale = np.abs(z["out_quarter"]).max()
+    assert np.abs(out["orig_size_logits"].numpy() - z["out_quarter"]).max() <= 1e-5 * scale
+    assert np.abs(out["logits"].numpy()[:, :, ::7, ::5] - z["out_logits_sample"]).max() <= 1e-5 * scale
+    assert (out["seg"].numpy() != z["out_seg"]).mean() <= 1e-3
+    ls = bg_oracle.loss(sd, inp, {"seg": target}, dense=True)
+    assert abs(ls["loss"].item() - float(z["loss"])) <= 1e-5 * float(z["loss"])
+    assert abs(ls["accuracy"].item() - float(z["accuracy"])) <= 1e-4
+    z = np.load(os.path.join(GOLD, "loss_iid64.npz"))
+    sd, inp, target = golden_dense_inputs(z, bg_shapes, dense=False)
+    ls = bg_oracle.loss(sd, inp, {"seg": target})
+    assert abs(ls["loss"].item() - float(z["loss"])) <= 1e-5 * float(z["loss"])
+    assert abs(ls["accuracy"].item() - float(z["accuracy"])) <= 1e-4
+
+
 def test_scatter_tie_rule_known_answer():
     """Two sources land in the same cell with equal depth: the lower flattened source index wins
     (torch_scatter CPU rule); invalid-only cells get label 0 and depth max+1; untouched cells -1."""
