@@ -634,7 +634,7 @@ static int first_conv_maps(FirstMaps* p, const uint8_t* labels, const float* dep
 struct PoolParams {
   const void* in; const void* in_lo; int in_cs; size_t in_img;
   void* out; void* out_lo; int out_cs; size_t out_img;
-  int b, Ho, Wo, c4, split;
+  int b, Ho, Wo, Wi, c4, split;      // Wi: input row length (2 * Wo, or 2 * Wo + 1: the pool floors)
 };
 
 // grid = (ceil(Wo * groups / 256), Ho, b): one thread per (output pixel, 8-channel group)
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(PoolParams p) {
   if (idx >= p.Wo * p.c4) return;
   const int x = idx / p.c4, c = idx - x * p.c4;
   const int y = blockIdx.y, img = blockIdx.z;
-  const int Wi = p.Wo * 2;
+  const int Wi = p.Wi;
   const size_t p0 = (size_t)img * p.in_img + ((size_t)(2 * y) * Wi + 2 * x) * p.in_cs + c * 8;
   float a[8], bq[8], cq[8], d[8], o[8];
   load8_any(p.in, p.in_lo, p0, sp, a);
@@ -1262,6 +1262,24 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     L->add_pbytes = 0;                                       // no room for the staged patches: per-pixel gathers
     if (!halo_plan_smem(L, smem)) return 1;
   }
+  if (!L->fold && !L->resident) {
+    // streamed weights: with 64-channel chunks the activation ring is 2 deep (46 KB per stage) -- the load of chunk
+    // j + 2 only starts when chunk j's MMAs have drained -- and an N tile >= 96 leaves 3-5 weight stages of 24-32 KB.
+    // 32-channel chunks halve both: 4 activation stages + 8 weight stages.  Measured per 16 frames, all streamed layers
+    // on 32-channel chunks: 196->88 119 -> 110 us, 294->118 71 -> 63, 401->118 89 -> 81, 108->46 (then folded in three
+    // 16-cout CTAs) 189 -> 173, but 235->52 101 -> 113, 267->24 33 -> 38: the N = 64 layers keep 6-7 weight stages with
+    // wide chunks and only pay the extra boxes.  Default: N tile >= 96 or 48.  A/B PF_HALO_STREAM_W=64 / 32: all wide / narrow.
+    const char* sw = getenv("PF_HALO_STREAM_W");
+    const int wmax = sw && sw[0] ? atoi(sw) : ((ntile >= 96 || ntile == 48) ? 32 : 64);
+    if (wmax < 64) {
+      HaloLayer V = *L;
+      size_t sm2 = 0;
+      bool any = false;
+      for (int k = 0; k < V.nseg; ++k)
+        if (V.seg_w[k] > wmax) { V.seg_w[k] = wmax; any = true; }
+      if (any && halo_plan_smem(&V, &sm2) && !V.resident && V.stages_a > L->stages_a) { *L = V; *smem = sm2; }
+    }
+  }
   if (!L->fold && !no_fold && c.ksize == 3 && L->tap_mask == 0x1FF && ntile == 48 && c.coutpad == 48 && kin >= fold_min_k &&
       !L->resident) {
     // 48 couts whose weights have to be streamed per tile: three folded CTAs of 16 couts with resident weights instead
@@ -1301,6 +1319,31 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     rc = halo_encode_weight_map(&m, net->wtc_dev[i] + (size_t)nrows * ktot, ktot, nrows, ntile, w);
     if (rc) return rc;
     maps->push_back(m);
+  }
+  {
+    // CTA pairs for the layers whose weights are streamed per (chunk, tap): at 1/16 resolution and below every tile
+    // pulls the layer's whole weight matrix (0.3 - 2.3 MB) from L2, ~40 B per clock and SM when the MMAs are to stay
+    // busy, and all 148 SMs do so at once.  The hypothesis was that the L2 -> SM fabric bounds them.  A pair shares one
+    // weight stream: each CTA loads half of every tile and TMA multicast delivers it to both.  MEASURED (batch 16): 3-8 %
+    // SLOWER on every streamed layer (196->88 119 -> 124 us, 144->52 81 -> 88, 235->52 102 -> 108): the L2 -> SM fabric
+    // is not what bounds them, and the pair runs in lock step.  Opt-in (PF_HALO_CLUSTER=1), tested.
+    const char* cl = getenv("PF_HALO_CLUSTER");
+    const bool want = cl && cl[0] == '1';
+    const int tiles = cdiv(io.Wout, 8) * cdiv(io.Hout, 16) * io.b;
+    L->cluster = (want && !L->resident && !L->fold && ntile % 16 == 0 && tiles >= 2 && kNumSMs / nb >= 2) ? 1 : 0;
+    for (int k = 0; k < 3; ++k) {
+      L->w_map_half[k] = -1;
+      if (!L->cluster || !used[k]) continue;
+      const int w = 16 << k;
+      L->w_map_half[k] = (int)maps->size();
+      CUtensorMap m;
+      int rc = halo_encode_weight_map(&m, net->wtc_dev[i], ktot, nrows, ntile / 2, w);
+      if (rc) return rc;
+      maps->push_back(m);
+      rc = halo_encode_weight_map(&m, net->wtc_dev[i] + (size_t)nrows * ktot, ktot, nrows, ntile / 2, w);
+      if (rc) return rc;
+      maps->push_back(m);
+    }
   }
   *nblocks = nb;
   {
@@ -1617,8 +1660,14 @@ extern "C" int pf_bgnet_set_depth_norm(pf_bgnet_t* net, float mean, float std) {
   return 0;
 }
 
+// Input sizes the plan handles: the two stride-2 convs need H/2 and H/4 exact (the reference's ceil == floor then,
+// hardnet.py ConvLayer padding k//2), the four AvgPool2d(2,2) floor like the arena's `>> shift`, TransitionUp goes to
+// the skip tensor's size whatever the ratio; W % 16: the uint8 label / mask tensor maps of the first conv need 16-byte
+// row pitches.  At least one pixel must be left at 1/64 resolution.
+static bool size_supported(int H, int W) { return H >= 64 && W >= 64 && H % 4 == 0 && W % 16 == 0; }
+
 extern "C" size_t pf_bgnet_workspace_bytes(const pf_bgnet_t* net, int b, int H, int W) {
-  if (!net || b <= 0 || H <= 0 || W <= 0 || H % 64 || W % 64) return 0;
+  if (!net || b <= 0 || !size_supported(H, W)) return 0;
   Arena a;
   make_arena(net, nullptr, b, H, W, &a);
   return a.total_bytes;
@@ -1664,8 +1713,8 @@ static int bgnet_forward_impl(pf_bgnet_t* net, const uint8_t* labels_dev, const 
                               float* out_full_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   PF_REQUIRE(net && (labels_dev || scores_dev) && workspace_dev, PF_EINVAL, "pf_bgnet_forward: null pointer");
   PF_REQUIRE(!net->use_depth || (depth_dev && mask_dev), PF_EINVAL, "pf_bgnet_forward: depth inputs required");
-  PF_REQUIRE(b > 0 && H > 0 && W > 0 && H % 64 == 0 && W % 64 == 0, PF_EINVAL,
-             "pf_bgnet_forward: H and W must be positive multiples of 64 (got %dx%d)", H, W);
+  PF_REQUIRE(b > 0 && size_supported(H, W), PF_EINVAL,
+             "pf_bgnet_forward: H must be a multiple of 4, W a multiple of 16, both >= 64 (got %dx%d)", H, W);
   PF_REQUIRE(final_h > 0 && final_w > 0, PF_EINVAL, "pf_bgnet_forward: bad final size");
   PF_REQUIRE(workspace_bytes >= pf_bgnet_workspace_bytes(net, b, H, W), PF_ENOMEM, "pf_bgnet_forward: workspace too small");
   for (auto& c : net->convs) PF_REQUIRE(c.loaded, PF_ESTATE, "pf_bgnet_forward: weights of %s not loaded", c.name.c_str());
@@ -1749,7 +1798,7 @@ static int bgnet_forward_impl(pf_bgnet_t* net, const uint8_t* labels_dev, const 
         p.in = a.ptr(in.buf, in.coff); p.in_lo = a.ptr_lo(in.buf, in.coff); p.in_cs = ib.cstride; p.in_img = a.img_elems[in.buf];
         p.out = a.ptr(s.out.buf, s.out.coff); p.out_lo = a.ptr_lo(s.out.buf, s.out.coff); p.out_cs = ob.cstride;
         p.out_img = a.img_elems[s.out.buf];
-        p.b = b; p.Ho = H >> ob.shift; p.Wo = W >> ob.shift; p.c4 = in.cpad() / 8; p.split = split;
+        p.b = b; p.Ho = H >> ob.shift; p.Wo = W >> ob.shift; p.Wi = W >> ib.shift; p.c4 = in.cpad() / 8; p.split = split;
         avgpool2_kernel<<<dim3(cdiv(p.Wo * p.c4, 256), p.Ho, b), 256, 0, st>>>(p);
         PF_CHECK_CUDA(cudaGetLastError());
         break;

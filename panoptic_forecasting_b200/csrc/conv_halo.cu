@@ -74,10 +74,20 @@ struct ChunkIssue {
   uint32_t smem_base, ntile4;             // resident weights: tap tiles [hi rows ; lo rows] are align1k(4 * ntile * W) bytes apart
   uint32_t b_base, b_tile, bar_full_b0, bar_empty_b0;
   int SB;
+  uint32_t mc;                  // HaloLayer::cluster: the streamed weight ring is shared by the CTA pair (see the producer)
 };
 
+// position in the streamed-weight ring: stage index and the parity its full barrier is waited on.  Kept incrementally:
+// `ib % SB` and `ib / SB` with a run-time SB are ~40 dependent instructions, and they sat in the issuing thread between
+// the MMAs of consecutive taps (the tensor pipe idles while its issuer computes, see mma_warp_loop)
+struct BCursor { int idx; uint32_t ph; };
+__device__ __forceinline__ void bcur_advance(BCursor& b, int n, int SB) {
+  b.idx += n;
+  while (b.idx >= SB) { b.idx -= SB; b.ph ^= 1u; }
+}
+
 template <int W, int NK, int KS, bool RES>
-__device__ __forceinline__ void issue_chunk(const ChunkIssue& c, uint32_t acc_first, uint32_t& woff, int& ib) {
+__device__ __forceinline__ void issue_chunk(const ChunkIssue& c, uint32_t acc_first, uint32_t& woff, BCursor& ib) {
   constexpr int HX = KS == 1 ? 8 : 10;
   constexpr uint32_t RP = 2u * W;
   constexpr uint32_t LAY = W == 64 ? 2u : (W == 32 ? 4u : 6u);
@@ -96,11 +106,11 @@ __device__ __forceinline__ void issue_chunk(const ChunkIssue& c, uint32_t acc_fi
         sb = c.smem_base + woff;
         woff += align1k(c.ntile4 * (uint32_t)W);
       } else {
-        sbi = ib % c.SB;
-        mbar_wait(c.bar_full_b0 + 8u * sbi, (ib / c.SB) & 1);
+        sbi = ib.idx;
+        mbar_wait(c.bar_full_b0 + 8u * sbi, ib.ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         sb = c.b_base + sbi * c.b_tile;
-        ++ib;
+        if (++ib.idx == c.SB) { ib.idx = 0; ib.ph ^= 1u; }
       }
       const uint32_t b_lo = ((sb & 0x3FFFFu) >> 4) | (1u << 16);
 #pragma unroll
@@ -109,7 +119,11 @@ __device__ __forceinline__ void issue_chunk(const ChunkIssue& c, uint32_t acc_fi
         umma_bf16_w(c.d, a_hi_lo + shift, A_HI, b_lo + 2 * ka, B_HI, c.idesc2, (dx == 0 && ka == 0) ? accv : 1u, c.el);
         umma_bf16_w(c.d, a_lo_lo + shift, A_HI, b_lo + 2 * ka, B_HI, c.idesc1, 1u, c.el);
       }
-      if (!RES) umma_commit_p(c.bar_empty_b0 + 8u * sbi, c.el);
+      if (!RES) {
+        // the stage goes back to BOTH producers of a CTA pair: each of them writes its half of the next tile into both CTAs
+        if (c.mc) umma_commit_mc_p(c.bar_empty_b0 + 8u * sbi, (uint16_t)3, c.el);
+        else umma_commit_p(c.bar_empty_b0 + 8u * sbi, c.el);
+      }
     }
     a_hi_lo += (uint32_t)(HX * (int)(RP >> 4));
     a_lo_lo += (uint32_t)(HX * (int)(RP >> 4));
@@ -123,7 +137,7 @@ __host__ __device__ __forceinline__ uint32_t chunk_code(int w, int nk, int seg, 
 }
 
 template <int KS, bool RES>
-__device__ __forceinline__ void issue_dispatch(uint32_t code, const ChunkIssue& ci, uint32_t accf, uint32_t& woff, int& ib) {
+__device__ __forceinline__ void issue_dispatch(uint32_t code, const ChunkIssue& ci, uint32_t accf, uint32_t& woff, BCursor& ib) {
   switch (code & 0xFFFu) {
     case 64u | (4u << 8): issue_chunk<64, 4, KS, RES>(ci, accf, woff, ib); break;
     case 64u | (3u << 8): issue_chunk<64, 3, KS, RES>(ci, accf, woff, ib); break;
@@ -177,7 +191,7 @@ __device__ __forceinline__ void issue_dispatch_fold(uint32_t code, const ChunkIs
 
 struct MmaCtx {
   uint32_t el, tmem_d, smem_base, a_base, a_tile, b_base, b_tile, bar0, idesc1, idesc2;
-  int total_tiles;
+  int total_tiles, rounds;
   bool dbg;
 };
 
@@ -201,9 +215,11 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
   ci.smem_base = m.smem_base; ci.ntile4 = (uint32_t)ntile * 4u;
   ci.b_base = m.b_base; ci.b_tile = m.b_tile;
   ci.bar_full_b0 = m.bar0 + 8u * (2 * kMaxA); ci.bar_empty_b0 = m.bar0 + 8u * (2 * kMaxA + kMaxB); ci.SB = L.stages_b;
-  const int my_tiles = (m.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  ci.mc = L.cluster ? 1u : 0u;
+  const int my_tiles = m.rounds;
   const int last_ia = my_tiles * nchunk - 1;
-  int ia = 0, ib = 0, st = 0, acc = 0;
+  int ia = 0, st = 0, acc = 0;
+  BCursor ib = {0, 0u};
   uint32_t ph_a = 0, ph_t = 1;
   long long wait_full = 0, wait_tmem = 0, w0 = 0;
   const bool dbg = m.dbg && role == 0;
@@ -239,7 +255,7 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
         const uint32_t w = code & 0xFFu;
         if (FOLD) woff += 3u * align1k(3u * ci.ntile4 * w);
         else if (RES) woff += (uint32_t)(KS * KS) * align1k(ci.ntile4 * w);
-        else ib += KS * KS;
+        else bcur_advance(ib, KS * KS, ci.SB);
       }
       if (++st == SA) { st = 0; ph_a ^= 1u; }
     }
@@ -286,12 +302,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
   const int tiles_per_img = L.tiles_x * L.tiles_y;
   const int total_tiles = tiles_per_img * L.batch;
   const float inv_tpi = 1.0f / (float)tiles_per_img, inv_tx = 1.0f / (float)L.tiles_x;
+  // CTA pair (HaloLayer::cluster, streamed weights): both CTAs run the SAME number of rounds, because every weight tile
+  // is loaded half by each of them into both; the odd CTA's last round may be a ghost tile (computed, not stored)
+  const uint32_t crank = L.cluster ? cluster_ctarank() : 0u;
+  const int bx0 = L.cluster ? ((int)blockIdx.x & ~1) : (int)blockIdx.x;
+  const int rounds = (total_tiles - bx0 + (int)gridDim.x - 1) / (int)gridDim.x;
   const int HX = L.hx, HY = L.hy, NT = L.taps;     // 3x3: 10 x 18 box, 9 taps; 1x1: 8 x 16 box, 1 tap
   const int org = NT == 9 ? 1 : 0;                  // box origin = tile origin - pad
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), L.cluster ? 2 : 1); }   // pair: both CTAs' MMA warps release a stage
     mbar_init(wbar, 1);
     // both MMA warps commit to tmem_full after their last chunk of a tile (a commit only covers the issuing thread's MMAs)
     const uint32_t nepi = MODE == 3 ? 4u : 4u * (uint32_t)(L.epi8 ? L.epi8 : 1);   // epilogue warps that hand a buffer back (epi8 = teams)
@@ -306,6 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (L.cluster) cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_smem;
   if (dbg && threadIdx.x == 0) L.dbg_ts[1] = clock64();
@@ -348,11 +370,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       }
       // ... and do not read the previous layer's activations before it has completed and flushed.
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      int ia = 0, ib = 0, st = 0, tp = 0;
+      int ia = 0, sb = 0, st = 0, tp = 0;
+      uint32_t ph_b = 1;                      // same bookkeeping for the streamed-weight ring
       uint32_t ph_a = 1;                      // parity to wait on for "stage free"; flips when the ring wraps
       long long wait_acc = 0;
       const int nchunk = L.nchunk;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int rd = 0, t0 = blockIdx.x; rd < rounds; ++rd, t0 += gridDim.x) {
+        const int t = t0 < total_tiles ? t0 : total_tiles - 1;      // ghost round of a CTA pair: any valid tile
         const int img = fast_div(t, tiles_per_img, inv_tpi);
         const int r = t - img * tiles_per_img;
         const int ty = fast_div(r, L.tiles_x, inv_tx), tx = r - ty * L.tiles_x;
@@ -393,16 +417,33 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
             const uint32_t b_tx = (uint32_t)ntile * 2u * w;
             for (int tap = 0; tap < NT; ++tap) {
               if (!((L.tap_mask >> tap) & 1)) continue;
-              const int sb = ib % SB;
-              mbar_wait(empty_b(sb), ((ib / SB) & 1) ^ 1);
+              mbar_wait(empty_b(sb), ph_b);
               const uint32_t sbp = b_base + sb * b_tile;
               mbar_expect_tx_p(full_b(sb), 2 * b_tx, el);
               const int koff = L.seg_koff[s] + tap * cpad + c0;
-              tma_load_2d_p(sbp, wm, full_b(sb), koff, n0, el);
-              tma_load_2d_p(sbp + b_tx, wm + 1, full_b(sb), koff, n0, el);
-              ++ib;
+              if (L.cluster) {
+                // CTA pair: this CTA fetches half of the tile's rows (of the hi and of the lo block) and TMA multicast
+                // writes them into both CTAs' rings -- every weight byte crosses L2 -> SM once per pair.  The stage was
+                // released by both MMA warps (empty_b counts 2); each CTA's full_b expects the whole tile.
+                const int hrows = ntile >> 1;
+                const uint32_t hoff = crank * (uint32_t)hrows * 2u * (uint32_t)w;
+                const CUtensorMap* wh = maps + L.w_map_half[w >> 5];
+                tma_load_2d_mc_p(sbp + hoff, wh, full_b(sb), koff, n0 + (int)crank * hrows, (uint16_t)3, el);
+                tma_load_2d_mc_p(sbp + b_tx + hoff, wh + 1, full_b(sb), koff, n0 + (int)crank * hrows, (uint16_t)3, el);
+              } else {
+                tma_load_2d_p(sbp, wm, full_b(sb), koff, n0, el);
+                tma_load_2d_p(sbp + b_tx, wm + 1, full_b(sb), koff, n0, el);
+              }
+              if (++sb == SB) { sb = 0; ph_b ^= 1u; }
             }
           }
+        }
+      }
+      if (L.cluster) {
+        // tail: every stage's last release has arrived (from both CTAs) before this CTA may exit
+        for (int k = 0; k < SB; ++k) {
+          mbar_wait(empty_b(sb), ph_b);
+          if (++sb == SB) { sb = 0; ph_b ^= 1u; }
         }
       }
       if (dbg && el) L.dbg_ts[11] = wait_acc;
@@ -424,7 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       if (dbg && el && role == 0) L.dbg_ts[2] = clock64();
       MmaCtx mc;
       mc.el = el; mc.tmem_d = tmem_d; mc.smem_base = smem_base; mc.a_base = a_base; mc.a_tile = a_tile;
-      mc.b_base = b_base; mc.b_tile = b_tile; mc.bar0 = bar0; mc.total_tiles = total_tiles; mc.dbg = dbg;
+      mc.b_base = b_base; mc.b_tile = b_tile; mc.bar0 = bar0; mc.total_tiles = total_tiles; mc.rounds = rounds; mc.dbg = dbg;
       mc.idesc1 = idesc1; mc.idesc2 = idesc2;
       const int ks = NT == 1 ? 1 : (L.tap_mask == 0x1FF ? 3 : 2);
       if (L.fold) {
@@ -465,23 +506,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           bias_w[k][i] = (MODE == 1 && (team + k * gs) * 16 < ntile && ch < L.cout_store) ? __ldg(L.bias + ch) : 0.f;
         }
     }
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc_) {
+    for (int t0 = blockIdx.x; tc_ < rounds; t0 += gridDim.x, ++tc_) {
       const int acc = tc_ & 1;
       if (MODE == 3 && acc != team) continue;      // alternate-tile teams: the other team's tile (and accumulator buffer)
+      const bool ghost = t0 >= total_tiles;        // CTA pair, last round of the odd CTA: drained, nothing stored
+      const int t = ghost ? total_tiles - 1 : t0;
       const int img = fast_div(t, tiles_per_img, inv_tpi);
       const int r = t - img * tiles_per_img;
       const int ty = fast_div(r, L.tiles_x, inv_tx), tx = r - ty * L.tiles_x;
       // fold: accumulator row m = input column x' = m & 15 of row m >> 4; output column = x' - 1 + tile origin
       const int oy = L.fold ? ty * 8 + (m >> 4) : ty * 16 + (m >> 3);
       const int ox = L.fold ? tx * 14 + (m & 15) - 1 : tx * 8 + (m & 7);
-      const bool inside = (oy < L.Hout) && (ox < L.Wout) && (!L.fold || ((m & 15) >= 1 && (m & 15) <= 14));
+      const bool inside = !ghost && (oy < L.Hout) && (ox < L.Wout) && (!L.fold || ((m & 15) >= 1 && (m & 15) <= 14));
       if (dbg) w0 = clock64();
       mbar_wait(tmem_full(acc), (tc_ >> 1) & 1);
       if (dbg) wait_epi += clock64() - w0;
       if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // pool: the even/even pixel of each 2x2 block stores the average, into the half-resolution tensor
-      const bool store_px = L.pool ? (((m & 9) == 0) && (oy >> 1) < (L.Hout >> 1) && (ox >> 1) < (L.Wout >> 1)) : inside;
+      const bool store_px = L.pool ? (!ghost && ((m & 9) == 0) && (oy >> 1) < (L.Hout >> 1) && (ox >> 1) < (L.Wout >> 1)) : inside;
       const size_t pix = L.s2d_block
                              ? (size_t)img * L.out_img_stride + ((size_t)(oy >> 1) * (L.Wout >> 1) + (ox >> 1)) * L.out_cs +
                                    (size_t)((oy & 1) * 2 + (ox & 1)) * L.s2d_block
@@ -691,6 +734,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (L.cluster) cluster_sync_all();       // neither CTA of a pair leaves while the other may still signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)L.tmem_cols));
   }
@@ -812,10 +856,15 @@ bool halo_plan_smem(HaloLayer* L, size_t* smem_bytes) {
   L->resident = 0;
   L->w_bytes_total = 0;
   L->w_tx_total = 0;
-  L->stages_a = 2;
-  const size_t rest = budget - 2 * (2 * a_tile);
-  int sb = (int)(rest / b_tile);
-  if (sb < 2) return false;
+  // streamed weights: the deepest activation ring (<= 4) that still leaves >= 6 weight stages; 2 when none does
+  int sa = 4, sb = 0;
+  for (; sa >= 2; --sa) {
+    if ((size_t)sa * 2 * a_tile + 2 * b_tile > budget) continue;
+    sb = (int)((budget - (size_t)sa * 2 * a_tile) / b_tile);
+    if (sb >= 6 || sa == 2) break;
+  }
+  if (sa < 2 || sb < 2) return false;
+  L->stages_a = sa;
   L->stages_b = sb > kMaxB ? kMaxB : sb;
   *smem_bytes = (size_t)L->stages_a * 2 * a_tile + (size_t)L->stages_b * b_tile + patches + 1024;
   return true;
@@ -841,6 +890,10 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   int gx = kNumSMs / nblocks;
   if (gx < 1) gx = 1;
   if (gx > total_tiles) gx = total_tiles;
+  if (L.cluster) {
+    gx &= ~1;                                   // CTA pairs along x
+    PF_REQUIRE(gx >= 2 && !L.resident && !L.fold, PF_ESTATE, "halo kernel: bad CTA-pair plan");
+  }
   static int use_pdl = -1;
   if (use_pdl < 0) { const char* e = getenv("PF_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
@@ -848,11 +901,20 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   cfg.blockDim = dim3(L.alt ? kHaloThreads8 : L.epi8 >= 4 ? kHaloThreads16 : (L.epi8 ? kHaloThreads8 : kHaloThreads));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr_pdl[1];
-  attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr_pdl[2];
+  int na = 0;
+  if (use_pdl) {
+    attr_pdl[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr_pdl[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (L.cluster) {
+    attr_pdl[na].id = cudaLaunchAttributeClusterDimension;
+    attr_pdl[na].val.clusterDim.x = 2; attr_pdl[na].val.clusterDim.y = 1; attr_pdl[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr_pdl;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   if (L.alt) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 3>, L, maps_dev));
   else if (L.epi8 >= 4) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads16, 1>, L, maps_dev));
   else if (L.epi8 && L.fold) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 2>, L, maps_dev));

@@ -51,6 +51,8 @@ struct HaloLayer {
   int amax_ncls;            // > 0 (fp32 head only): channel 15 of every stored pixel carries argmax over the first amax_ncls channels (int bits)
   int pool;                 // 2x2 average pool fused into the epilogue: out_* address the pooled tensor (Hout/2 x Wout/2)
   int epi8;                 // epilogue teams of 4 warps (0 = one; 2 / 4: extra teams share the TMEM lane quarters and take the other 16-channel groups)
+  int cluster;              // streamed weights: CTA pairs (cluster 2 x 1 x 1) share the weight ring, each CTA loads half of every tile and TMA multicast writes it into both
+  int w_map_half[3];        // weight tensor maps with a box of ntile / 2 rows (hi; lo = +1) for the pair's half loads
   int alt;                  // ntile <= 32: two epilogue teams on alternate tiles (team k owns accumulator buffer k); excludes epi8
   int fold;                 // 3x3, ntile <= 32, resident: the three taps of a filter row folded into N (10 x 16 box, 8 x 14 output tiles)
   uint32_t w_bytes_total, w_tx_total;

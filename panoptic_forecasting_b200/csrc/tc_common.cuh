@@ -168,5 +168,33 @@ static __device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t pred
                : "memory");
 }
 
+// ---- thread-block cluster helpers (weight-tile multicast of the halo kernel's streamed layers) ----
+static __device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of every CTA of the cluster
+static __device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose box lands at the same shared-memory offset of EVERY CTA in `mask`, each destination CTA's mbarrier (same
+// offset) receiving the complete_tx for the bytes
+static __device__ __forceinline__ void tma_load_2d_mc_p(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                         uint16_t mask, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask), "r"(pred)
+      : "memory");
+}
+// commit that arrives on the mbarrier at the same offset in every CTA of `mask`
+static __device__ __forceinline__ void umma_commit_mc_p(uint32_t bar, uint16_t mask, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+               ::"r"(bar), "h"(mask), "r"(pred)
+               : "memory");
+}
+
 }  // namespace tc
 }  // namespace pf

@@ -169,7 +169,7 @@ class BGModel(BaseModel):
         fh, fw = self.final_size if self.final_size is not None else (H, W)
         nbytes = self._lib.pf_bgnet_workspace_bytes(self._net, b, H, W)
         if nbytes == 0:
-            raise ValueError("unsupported input size %dx%d (H and W must be multiples of 64)" % (H, W))
+            raise ValueError("unsupported input size %dx%d (H must be a multiple of 4, W of 16, both >= 64)" % (H, W))
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         seg8 = seg64 = full = quarter = None

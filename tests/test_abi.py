@@ -36,7 +36,9 @@ def test_workspace_queries_and_arg_checks(pf_lib):
     assert pf_lib.pf_bgnet_create(C.byref(net), 99, 3, 1, 0) == -1
     assert pf_lib.pf_bgnet_create(C.byref(net), 11, 3, 1, 0) == 0
     try:
-        assert pf_lib.pf_bgnet_workspace_bytes(net, 1, 100, 128) == 0        # not a multiple of 64
+        assert pf_lib.pf_bgnet_workspace_bytes(net, 1, 102, 128) == 0        # H not a multiple of 4
+        assert pf_lib.pf_bgnet_workspace_bytes(net, 1, 128, 72) == 0         # W not a multiple of 16
+        assert pf_lib.pf_bgnet_workspace_bytes(net, 1, 100, 176) > 0
         assert pf_lib.pf_bgnet_workspace_bytes(net, 1, 1024, 2048) > 100e6
         # null pointers are rejected before any CUDA call
         assert pf_lib.pf_bgnet_forward(net, None, None, None, 1, 64, 64, 64, 64, None, None, None, None, None, 0, None) == -1

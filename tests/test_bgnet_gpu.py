@@ -139,6 +139,22 @@ def test_dense_planes_input_mode(pf_lib, bg_shapes, precision, tol):
         md.predict({"seg": lab.cuda(), "depth": inp["depth"].cuda(), "depth_mask": inp["depth_mask"].cuda()}, {})
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tc", 3e-4)])
+@pytest.mark.parametrize("h,w,final", [(68, 144, None), (100, 176, (200, 352)), (132, 80, None)])
+def test_sizes_not_multiples_of_64(pf_lib, bg_shapes, precision, tol, h, w, final):
+    """H % 4 == 0, W % 16 == 0: odd sizes at the pooled levels (AvgPool2d floors, hardnet.py:300; TransitionUp
+    interpolates to the skip's size, hardnet.py:249-255), ragged tiles everywhere."""
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=h)
+    inp = synthetic.make_bg_inputs(2, 3, h, w, seed=h)
+    q = bg_oracle.predict(sd, {k: v.clone() for k, v in inp.items()}, final)["orig_size_logits"]
+    sd["model.finalConv.bias"] = sd["model.finalConv.bias"] - q.mean((0, 2, 3))
+    ref = bg_oracle.predict(sd, {k: v.clone() for k, v in inp.items()}, final)
+    out = gpu_model(sd, final, precision=precision).predict({k: v.cuda() for k, v in inp.items()}, {})
+    check_against(out, ref, rel_tol=tol)
+    with pytest.raises(ValueError):
+        gpu_model(sd, precision=precision).predict({k: v[..., :66, :w].cuda() for k, v in inp.items()}, {})
+
+
 def test_every_conv_layer_vs_torch(pf_lib, bg_shapes):
     """Each of the 69 ConvLayers + finalConv through pf_bgnet_debug_conv vs F.conv2d + BN + ReLU."""
     sd = synthetic.make_bg_state_dict(bg_shapes, seed=2)

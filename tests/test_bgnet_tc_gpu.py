@@ -14,7 +14,7 @@ from test_bgnet_gpu import check_against, gpu_model
 pytestmark = pytest.mark.gpu
 
 
-def layer_sweep(pf_lib, bg_shapes, tol, hw=(24, 40)):
+def layer_sweep(pf_lib, bg_shapes, tol, hw=(24, 40), b=2):
     sd = synthetic.make_bg_state_dict(bg_shapes, seed=2)
     m = gpu_model(sd, precision="tc")
     m._upload(torch.device("cuda", torch.cuda.current_device()))
@@ -26,13 +26,13 @@ def layer_sweep(pf_lib, bg_shapes, tol, hw=(24, 40)):
         assert pf_lib.pf_bgnet_conv_info(m._net, i, C.byref(info)) == 0
         name = info.name.decode()
         H, W = hw if info.stride == 1 else (hw[0], hw[1] + 8)
-        x = torch.randn(2, info.cin, H, W, generator=g).relu()
+        x = torch.randn(b, info.cin, H, W, generator=g).relu()
         if i < n:
             ref = bg_oracle.conv_layer(sd, name, x, info.ksize, info.stride)
         else:
             ref = F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"])
         y = torch.empty(ref.shape, device="cuda")
-        rc = pf_lib.pf_bgnet_debug_conv(m._net, i, x.cuda().data_ptr(), 2, H, W, y.data_ptr(), None)
+        rc = pf_lib.pf_bgnet_debug_conv(m._net, i, x.cuda().data_ptr(), b, H, W, y.data_ptr(), None)
         assert rc == 0, (name, pf_lib.pf_last_error())
         err = (y.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
         assert err <= tol, (i, name, info.cin, info.cout, info.ksize, err)
@@ -71,6 +71,16 @@ def test_every_conv_layer_tcgen05_epilogue_teams(pf_lib, bg_shapes, monkeypatch,
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     layer_sweep(pf_lib, bg_shapes, 1e-4, hw=(100, 170))
+
+
+@pytest.mark.parametrize("cluster", ["1", "0"])
+def test_every_conv_layer_tcgen05_cta_pairs(pf_lib, bg_shapes, monkeypatch, cluster):
+    """Streamed-weight layers as CTA pairs (cluster 2x1x1, weight tiles loaded half by each CTA and multicast to both) and
+    without.  One image of 100 x 162: 147 tiles of 16 x 8 -> 146 CTAs, so CTA 1's second round is a ghost tile (its pair
+    partner still has a real one); the two-image sweeps above cover the even case."""
+    monkeypatch.delenv("PF_TC_FORCE_SIMT", raising=False)
+    monkeypatch.setenv("PF_HALO_CLUSTER", cluster)
+    layer_sweep(pf_lib, bg_shapes, 1e-4, hw=(100, 162), b=1)
 
 
 def test_every_conv_layer_tcgen05_unfolded(pf_lib, bg_shapes, monkeypatch):
