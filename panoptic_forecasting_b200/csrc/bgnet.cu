@@ -1231,7 +1231,9 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
   int kin = 0;
   for (int s = seg0; s < seg1; ++s) kin += c.in[s].cpad();
   const char* ff = getenv("PF_HALO_FOLD_MIN_K");
-  const int fold_min_k = ff && ff[0] ? atoi(ff) : 48;
+  // (round 2: with two epilogue teams on alternate tiles, HaloLayer::alt, the single-chunk layers fold too -- 18->10 at
+  // 1/4 resolution 117 -> 100 us, 28->16 at 1/8 40 -> 34 us per 16 frames; folded with ONE team they lose: 117 -> 123)
+  const int fold_min_k = ff && ff[0] ? atoi(ff) : 32;
   L->fold = (!no_fold && c.ksize == 3 && L->tap_mask == 0x1FF && ntile <= 32 && kin >= fold_min_k) ? 1 : 0;
   if (L->fold) {
     // The folded form needs resident weights and a ring of >= 3 activation stages.  A 32-cout layer whose weights
@@ -1370,7 +1372,9 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     const int alt = alt_auto ? 0 : atoi(al);
     if (L->ntile <= 32 && !L->add_pbytes && !L->add_src) {
       if (!L->fold && !L->epi8 && (alt & 1)) L->alt = 1;
-      if (L->fold && !L->epi8 && (alt & 2)) L->alt = 1;
+      // folded: only the K-light layers (one 32-channel chunk = 12 MMAs per tile) are bound by their epilogue; the
+      // others are tensor-bound and lose 2-6 us to the extra warps (76->28 274 -> 280, 73->18 210 -> 216)
+      if (L->fold && !L->epi8 && ((alt & 2) || (alt_auto && kin <= 32))) L->alt = 1;
       const bool one_small_chunk = L->nchunk == 1 && L->seg_cpad[0] == 16;
       if (!L->fold && L->epi8 == 2 && ((alt & 4) || (alt_auto && one_small_chunk))) { L->alt = 1; L->epi8 = 0; }
     }
