@@ -1241,7 +1241,19 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     // weights per SM; the activation boxes are fetched twice, from L2).
     const char* fs = getenv("PF_HALO_FOLD_SPLIT");
     const int split_mode = fs && fs[0] ? atoi(fs) : 1;       // 0 never, 1 when n = 32 does not fit, 2 always
-    bool planned = plan_fold(L, smem);                       // false when the weights cannot be resident
+    bool planned = false;
+    {
+      // N tile of 24 for the 18- / 24-output-channel layers (slots are padded to 32): the folded MMAs get N = 144 / 80
+      // instead of 192 / 96 (72 + 52 instead of 96 + 56 cycles per K atom and filter row).  A/B PF_HALO_FOLD_N24=0.
+      const char* n24 = getenv("PF_HALO_FOLD_N24");
+      if (!(n24 && n24[0] == '0') && ntile == 32 && c.coutpad == 32 && c.cout <= 24 && !c.s2d_out) {
+        HaloLayer T = *L;
+        size_t sm2 = 0;
+        T.ntile = 24;
+        if (plan_fold(&T, &sm2) && T.stages_a >= 3) { *L = T; *smem = sm2; ntile = 24; planned = true; }
+      }
+    }
+    if (!planned) planned = plan_fold(L, smem);              // false when the weights cannot be resident
     const bool roomy = planned && L->stages_a >= 3;
     // measured (batch 8): 135->28 at 1/8 (weights not resident at n = 32) 115 -> 77 us, 96->18 / 114->30 at 1/16
     // (resident with 2 stages, 4 tiles per SM) 31 -> 22 / 37 -> 27 us, but 91->28 at 1/4 (resident with 2 stages,

@@ -459,7 +459,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       // the epilogue adds the two column halves.  A (4 KB per MMA) is the shared-memory-bandwidth
       // bound of small-N layers, so reading A_hi once instead of twice is a 1.5x saving.
       const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
-      const uint32_t idesc1 = idesc_base | ((uint32_t)(((L.fold ? 3 : 1) * ntile) >> 3) << 17);
+      // (folded, n = 24: 3n = 72 is no UMMA N; the A_lo MMA runs with N = 80 and its last 8 columns pick up A_lo * W_lo of
+      // the dx = 0 block's first 8 channels -- the lo x lo product the scheme otherwise drops, 2^-16 relative)
+      const uint32_t idesc1 = idesc_base | ((uint32_t)((((L.fold ? 3 : 1) * ntile + 15) & ~15) >> 3) << 17);
       const uint32_t idesc2 = idesc_base | ((uint32_t)(((L.fold ? 6 : 2) * ntile) >> 3) << 17);
       if (L.resident) mbar_wait(wbar, 0);
       if (dbg && el && role == 0) L.dbg_ts[2] = clock64();
@@ -634,7 +636,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         // six 16-column pieces per 16 output channels: (hi, lo) parts of the dx = 0, 1, 2 blocks.  Output column x takes
         // block 0 from input column x - 1 (one lane down), block 1 from x, block 2 from x + 1 (one lane up); the 16
         // lanes of an accumulator row are one row of the tile, and lanes 0 / 15 of a row store nothing.
-        const int ng = (ntile == 32 && n0 + 16 < L.cout_store) ? 2 : 1;
+        const int ng = (ntile > 16 && n0 + 16 < L.cout_store) ? 2 : 1;
         if (MODE == 2 && team >= ng) release();           // a team without a group of its own
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -659,6 +661,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
             const float e2 = __uint_as_float(h2[i]) + __uint_as_float(l2[i]);
             const float left = __shfl_up_sync(0xffffffffu, e0, 1), right = __shfl_down_sync(0xffffffffu, e2, 1);
             v[i] = ((left + e1) + right) + bias_r[g][i];
+            // n = 24: columns 24..31 of a block are the next block's -- the slot's padding channels are written as zeros
+            if (g * 16 + i >= ntile) v[i] = 0.f;
           }
           finish16(v, n0 + g * 16);
         }
