@@ -1371,7 +1371,8 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     if (L->fold && L->ntile == 32 && ft && ft[0] == '1') L->epi8 = 2;
     const char* e16 = getenv("PF_HALO_EPI16");
     const bool never = e16 && e16[0] == '0', always = e16 && e16[0] == '1';
-    if (L->epi8 && L->ntile >= 64 && !never && (always || !L->add_pbytes)) L->epi8 = 4;
+    (void)always;                                          // (the four-team kernel no longer carries the additive term)
+    if (L->epi8 && L->ntile >= 64 && !never && !L->add_pbytes && !add_patch) L->epi8 = 4;
     // alternate-tile epilogue teams (conv_halo_kernel<352, 3>: team k owns accumulator buffer k) for N tiles <= 32.
     // Measured per 16 frames: base.1 (16->24 at 1/2 resolution, one 16-channel chunk = 18 MMAs per tile, the epilogue
     // is the whole cost) 500 -> 449 us against two column teams; no gain anywhere else -- the one-team K-light layers
@@ -1468,6 +1469,7 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
       HaloLayer& hl = P.halos[i];
       hl.add_src = lo.out_f32; hl.add_H = lo.Hout; hl.add_W = lo.Wout; hl.add_cs = lo.out_cs; hl.add_img = lo.out_img;
       hl.add_sh = sh; hl.add_sw = sw;
+      if (hl.epi8 >= 4) hl.epi8 = 2;                  // the four-team kernel has no additive-term path (gather form lands here)
       if (hl.add_pbytes) {
         CUtensorMap m;
         rc = halo_encode_add_map(&m, lo.out_f32, lo.out_cs, lo.Wout, lo.Hout, a.b, lo.out_img, hl.ntile);

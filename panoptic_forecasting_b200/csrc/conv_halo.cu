@@ -505,7 +505,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int ch = n0 + (team + k * gs) * 16 + i;
-          bias_w[k][i] = (MODE == 1 && (team + k * gs) * 16 < ntile && ch < L.cout_store) ? __ldg(L.bias + ch) : 0.f;
+          // (the four-team instantiation has 96 registers: it keeps only its first group's bias, a second group -- N tiles
+          // > 64 -- reads it through L1; holding both spilled 88 bytes per thread and cost base.5 193 -> 265 us)
+          bias_w[k][i] = (MODE == 1 && (k == 0 || THREADS <= 352) && (team + k * gs) * 16 < ntile && ch < L.cout_store) ? __ldg(L.bias + ch) : 0.f;
         }
     }
     for (int t0 = blockIdx.x; tc_ < rounds; t0 += gridDim.x, ++tc_) {
@@ -536,7 +538,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       const float *a00 = nullptr, *a01 = nullptr, *a10 = nullptr, *a11 = nullptr;
       uint32_t s00 = 0, s01 = 0, s10 = 0, s11 = 0;       // shared-memory addresses of the four source pixels (patch form)
       float aly = 0.f, alx = 0.f;
-      if (L.add_src && inside) {
+      // (the four-team instantiation never carries the additive term: its 96 registers have no room for the eight source
+      // addresses, and the fused conv1x1_up layers measured slower with four teams anyway)
+      if (THREADS <= 352 && L.add_src && inside) {
         const float fy = L.add_sh * (float)oy, fx = L.add_sw * (float)ox;
         const int ay0 = (int)fy, ax0 = (int)fx;
         const int ay1 = ay0 + (ay0 < L.add_H - 1 ? 1 : 0), ax1 = ax0 + (ax0 < L.add_W - 1 ? 1 : 0);
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           a10 = ab + ((size_t)ay1 * L.add_W + ax0) * L.add_cs; a11 = ab + ((size_t)ay1 * L.add_W + ax1) * L.add_cs;
         }
       }
-      if (L.add_pbytes) mbar_wait(full_p(acc), (tc_ >> 1) & 1);
+      if (THREADS <= 352 && L.add_pbytes) mbar_wait(full_p(acc), (tc_ >> 1) & 1);
       const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (L.fold ? 6 : 2) * ntile);
       // the accumulator buffer goes back to the MMA warps as soon as it has been READ (not after the stores):
       // with only two buffers the MMAs of tile i+2 otherwise wait for the whole epilogue of tile i
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         if (lane == 0) mbar_arrive(tmem_empty(acc));
       };
       auto finish16 = [&](float (&v)[16], const int n) {     // v = conv + bias of channels [n, n + 16)
-        if (s00) {
+        if (THREADS <= 352 && s00) {
           // four products per channel (the weights are per pixel): the interpolation costs 4 FMAs instead of 3 lerps
           const float w00 = (1.f - aly) * (1.f - alx), w01 = (1.f - aly) * alx, w10 = aly * (1.f - alx), w11 = aly * alx;
           const uint32_t co = (uint32_t)(n - n0) * 4u;
@@ -577,7 +581,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
             v[4 * i + 3] += fmaf(w00, p.w, fmaf(w01, q4.w, fmaf(w10, r4.w, w11 * s4.w)));
           }
         }
-        if (a00) {
+        if (THREADS <= 352 && a00) {
           const float ahy = 1.f - aly, ahx = 1.f - alx;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -711,13 +715,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           if (has2) { tmem_ld_wait16(r2); tmem_ld_wait16(r3); }
           if (g == last || (has2 && g2 == last)) release();
           float v[16];
-          // bias_w[0] / [1] = this warp's first / second group; in the one-group-per-round form the second group is the
-          // first slot of the second round
-          const bool second = THREADS > 352 && g != team;
+          // bias_w[0] / [1] = this warp's first / second group (two-group rounds).  One group per round (four teams): only
+          // the first group's bias is in registers
+          const bool first_in_regs = THREADS > 352 ? (MODE == 1 && g == team) : bias_in_regs;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) +
-                   (bias_in_regs ? (second ? bias_w[1][i] : bias_w[0][i]) : __ldg(L.bias + n0 + g * 16 + i));
+            v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + (first_in_regs ? bias_w[0][i] : __ldg(L.bias + n0 + g * 16 + i));
           finish16(v, n0 + g * 16);
           if (has2) {
 #pragma unroll
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         }
         if (last < 0) release();
       }
-      if (L.add_pbytes) {                       // the patch buffer goes back to the producer
+      if (THREADS <= 352 && L.add_pbytes) {     // the patch buffer goes back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_p(acc));
       }
