@@ -9,6 +9,8 @@ LIB = os.path.join(HERE, "libpf_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-shared", "-Xcompiler", "-fPIC"]
+if os.environ.get("PF_HALO_DBG") == "1":      # dev builds: halo-kernel timestamps / ablations for tools/halo_ts.py
+    FLAGS.append("-DPF_HALO_DBG")
 
 
 def sources():

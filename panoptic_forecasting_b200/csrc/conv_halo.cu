@@ -33,6 +33,14 @@ namespace pf {
 using namespace tc;
 
 namespace {
+// Phase timestamps / wait accounting / ablations (tools/halo_ts.py) are a BUILD option: -DPF_HALO_DBG.  As a run-time flag
+// they cost every tile of every epilogue warp an S2R, a 64-bit clock read and their scoreboard stalls (ncu source view of
+// conv1x1_up.3: 5 % of the samples) plus a dozen registers in instantiations that spill.
+#ifdef PF_HALO_DBG
+constexpr bool kHaloDbg = true;
+#else
+constexpr bool kHaloDbg = false;
+#endif
 constexpr int kMaxA = 8, kMaxB = 8;
 constexpr int kHaloThreads = 224, kHaloThreads8 = 352, kHaloThreads16 = 608;   // 1 / 2 / 4 epilogue teams      // warp 0 TMA producer, warps 1 and 6 MMA issuers, warps 2..5 (+ 7..10: HaloLayer::epi8) epilogue
 
@@ -222,7 +230,7 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
   BCursor ib = {0, 0u};
   uint32_t ph_a = 0, ph_t = 1;
   long long wait_full = 0, wait_tmem = 0, w0 = 0;
-  const bool dbg = m.dbg && role == 0;
+  const bool dbg = kHaloDbg && m.dbg && role == 0;
   for (int tl = 0; tl < my_tiles; ++tl) {
     if ((ia & 1) == role) {                   // owner of the tile's first chunk: the accumulator buffer must be drained
       if (dbg) w0 = clock64();
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const bool dbg = L.dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool dbg = kHaloDbg && L.dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   if (dbg && threadIdx.x == 0) L.dbg_ts[0] = clock64();
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int ntile = L.ntile;
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           if (dbg) wait_acc += clock64() - w0;
           if (dbg && el && ia < 24) L.dbg_ts[16 + ia] = clock64();
           const uint32_t sa = a_base + st * 2 * a_tile;
-          if ((L.dbg_mode & 1) && ia >= SA) {
+          if (kHaloDbg && (L.dbg_mode & 1) && ia >= SA) {
             if (el) mbar_arrive(full_a(st));
             __syncwarp();
           } else {
@@ -606,7 +614,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
             v[i] = t * 0.25f;
           }
         }
-        if (!store_px || (L.dbg_mode & 2)) return;
+        if (!store_px || (kHaloDbg && (L.dbg_mode & 2))) return;
         if (L.out_f32) {
           if (L.amax_ncls > 0 && n == 0) {
             // first maximum of the class logits (torch.argmax tie rule), parked in the padding channel for the

@@ -34,7 +34,20 @@ def main(csv_path, layers_path):
             d[n] = v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
         else:
             d[n] = v
-    convs = [l for l in meta["layers"] if l["type"] in ("conv", "head")]
+    # launch order: every ConvLayer is one conv_halo launch, except the four conv1x1_up layers, which (fused with their
+    # TransitionUp) are a low-resolution launch over the upsampled slices (fp32 partial sums out)
+    # followed by a high-resolution launch over the skip slices that interpolates the partial in its epilogue
+    skip_ch = [214, 160, 78, 48]
+    convs = []
+    for l in meta["layers"]:
+        if l["type"] not in ("conv", "head"):
+            continue
+        if l["name"].startswith("model.conv1x1_up."):
+            j = int(l["name"].split(".")[2])
+            convs.append(dict(l, part="low", cin=l["cin"] - skip_ch[j]))
+            convs.append(dict(l, part="high", cin=skip_ch[j]))
+        else:
+            convs.append(l)
     ci = 0
     pad = lambda c: (c + 15) // 16 * 16
     print("%-4s %-28s %-34s %-12s %9s %9s %9s %7s %8s %7s" % ("id", "kernel", "layer", "shape", "us", "dram MB", "algo MB", "x algo", "TFLOP/s", "tensor%"))
@@ -45,12 +58,17 @@ def main(csv_path, layers_path):
         if "conv_halo" in d["kernel"] and ci < len(convs):
             c = convs[ci]; ci += 1
             r = res_of(c["name"])
+            part = c.get("part")
+            if part == "low":
+                r *= 2
             px = batch * (H // r) * (W // r)
-            layer, shape = c["name"], "%d->%d k%d 1/%d" % (c["cin"], c["cout"], c["k"], r)
+            layer, shape = c["name"] + (" [%s]" % part if part else ""), "%d->%d k%d 1/%d" % (c["cin"], c["cout"], c["k"], r)
             out_b = pad(c["cout"]) * 4 * px / (4 if (c["k"] == 1 and c["name"].startswith("model.base.") and r < 64) else 1)
             if c["type"] == "head":
                 out_b = 16 * 4 * px
             algo = pad(c["cin"]) * 4 * px + out_b                 # split-bf16 storage: 4 B per element in and out
+            if part == "high":
+                algo += pad(c["cout"]) * 4 * px / 4               # + the fp32 partial sums of the low-resolution launch
             tfl = 2.0 * c["k"] * c["k"] * c["cin"] * c["cout"] * px / (d["us"] * 1e-6) / 1e12
         dram = d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
         tp = d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")

@@ -1,4 +1,5 @@
 """Dev tool (GPU box): phase timestamps / wait accounting of the halo kernel on full-size layers.
+Needs a library built with the instrumentation: PF_HALO_DBG=1 python -m panoptic_forecasting_b200.build --force
 PF_HALO_TS=1 python tools/halo_ts.py [layer indices...]"""
 import ctypes as C
 import os
