@@ -1469,7 +1469,7 @@ static int ensure_tc_plan(pf_bgnet* net, const Arena& a, const void* ws) {
       HaloLayer& hl = P.halos[i];
       hl.add_src = lo.out_f32; hl.add_H = lo.Hout; hl.add_W = lo.Wout; hl.add_cs = lo.out_cs; hl.add_img = lo.out_img;
       hl.add_sh = sh; hl.add_sw = sw;
-      if (hl.epi8 >= 4) hl.epi8 = 2;                  // the four-team kernel has no additive-term path (gather form lands here)
+      hl.epi8 = 2; hl.alt = 0;                        // the additive term lives in conv_halo_kernel<352, 1, true> only
       if (hl.add_pbytes) {
         CUtensorMap m;
         rc = halo_encode_add_map(&m, lo.out_f32, lo.out_cs, lo.Wout, lo.Hout, a.b, lo.out_img, hl.ntile);

@@ -276,7 +276,9 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
 // MODE 0: every epilogue path (one team); 1: wide path only (2 / 4 teams); 2: folded path only, two teams;
 // 3: the N <= 32 paths (folded / whole row in registers) with two teams that take ALTERNATE TILES (HaloLayer::alt): team k
 // owns accumulator buffer k, so the epilogue of tile i + 1 runs next to that of tile i instead of behind it
-template <int THREADS, int MODE>
+// ADD: the epilogue carries the additive term of the fused conv1x1_up layers (only <352, 1> is instantiated with it: its
+// eight source addresses and interpolation weights otherwise sit in the registers of every wide layer)
+template <int THREADS, int MODE, bool ADD = false>
 __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxB + 9];
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       float aly = 0.f, alx = 0.f;
       // (the four-team instantiation never carries the additive term: its 96 registers have no room for the eight source
       // addresses, and the fused conv1x1_up layers measured slower with four teams anyway)
-      if (THREADS <= 352 && L.add_src && inside) {
+      if (ADD && L.add_src && inside) {
         const float fy = L.add_sh * (float)oy, fx = L.add_sw * (float)ox;
         const int ay0 = (int)fy, ax0 = (int)fx;
         const int ay1 = ay0 + (ay0 < L.add_H - 1 ? 1 : 0), ax1 = ax0 + (ax0 < L.add_W - 1 ? 1 : 0);
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           a10 = ab + ((size_t)ay1 * L.add_W + ax0) * L.add_cs; a11 = ab + ((size_t)ay1 * L.add_W + ax1) * L.add_cs;
         }
       }
-      if (THREADS <= 352 && L.add_pbytes) mbar_wait(full_p(acc), (tc_ >> 1) & 1);
+      if (ADD && L.add_pbytes) mbar_wait(full_p(acc), (tc_ >> 1) & 1);
       const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (L.fold ? 6 : 2) * ntile);
       // the accumulator buffer goes back to the MMA warps as soon as it has been READ (not after the stores):
       // with only two buffers the MMAs of tile i+2 otherwise wait for the whole epilogue of tile i
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         if (lane == 0) mbar_arrive(tmem_empty(acc));
       };
       auto finish16 = [&](float (&v)[16], const int n) {     // v = conv + bias of channels [n, n + 16)
-        if (THREADS <= 352 && s00) {
+        if (ADD && s00) {
           // four products per channel (the weights are per pixel): the interpolation costs 4 FMAs instead of 3 lerps
           const float w00 = (1.f - aly) * (1.f - alx), w01 = (1.f - aly) * alx, w10 = aly * (1.f - alx), w11 = aly * alx;
           const uint32_t co = (uint32_t)(n - n0) * 4u;
@@ -589,7 +591,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
             v[4 * i + 3] += fmaf(w00, p.w, fmaf(w01, q4.w, fmaf(w10, r4.w, w11 * s4.w)));
           }
         }
-        if (THREADS <= 352 && a00) {
+        if (ADD && a00) {
           const float ahy = 1.f - aly, ahx = 1.f - alx;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -709,9 +711,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         const bool bias_in_regs = MODE == 1 && last >= 0 && last <= team + gstep;   // at most two groups: their bias sits in bias_w
         // two 16-channel groups per round: four TMEM loads in flight, one wait, and the accumulator buffer goes back
         // to the MMA warps right after this warp's last read
-        for (int g = team; g < ngroups; g += (THREADS <= 352 ? 2 : 1) * gstep) {
+        constexpr bool kTwo = THREADS <= 352 && !ADD;            // two groups per round (the four-team and the additive-term
+                                                                 // instantiations have no registers for it)
+        for (int g = team; g < ngroups; g += (kTwo ? 2 : 1) * gstep) {
           const int g2 = g + gstep;
-          const bool has2 = THREADS <= 352 && g2 < ngroups;      // the four-team instantiation (104 registers) takes one group per round
+          const bool has2 = kTwo && g2 < ngroups;
           uint32_t r0[16], r1[16], r2[16], r3[16];
           tmem_ld16_nowait(trow + (uint32_t)(g * 16), r0);
           tmem_ld16_nowait(trow + (uint32_t)(ntile + g * 16), r1);
@@ -725,10 +729,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           float v[16];
           // bias_w[0] / [1] = this warp's first / second group (two-group rounds).  One group per round (four teams): only
           // the first group's bias is in registers
-          const bool first_in_regs = THREADS > 352 ? (MODE == 1 && g == team) : bias_in_regs;
+          const bool first_in_regs = kTwo ? bias_in_regs : (MODE == 1 && g == team);
+          const bool second_in_regs = !kTwo && THREADS <= 352 && bias_in_regs && g == team + gstep;   // one group per round, second round
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + (first_in_regs ? bias_w[0][i] : __ldg(L.bias + n0 + g * 16 + i));
+            v[i] = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) +
+                   (first_in_regs ? bias_w[0][i] : second_in_regs ? bias_w[1][i] : __ldg(L.bias + n0 + g * 16 + i));
           finish16(v, n0 + g * 16);
           if (has2) {
 #pragma unroll
@@ -739,7 +745,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         }
         if (last < 0) release();
       }
-      if (THREADS <= 352 && L.add_pbytes) {     // the patch buffer goes back to the producer
+      if (ADD && L.add_pbytes) {                // the patch buffer goes back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_p(acc));
       }
@@ -898,6 +904,7 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
       PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       attr_done.fetch_or(bit, std::memory_order_release);
     }
   }
@@ -913,6 +920,8 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   if (use_pdl < 0) { const char* e = getenv("PF_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, nblocks);
+  const bool add = L.add_src != nullptr;        // additive term: the two-team wide instantiation only
+  PF_REQUIRE(!add || (L.epi8 == 2 && !L.fold && !L.alt), PF_ESTATE, "halo kernel: the additive term needs the two-team wide form");
   cfg.blockDim = dim3(L.alt ? kHaloThreads8 : L.epi8 >= 4 ? kHaloThreads16 : (L.epi8 ? kHaloThreads8 : kHaloThreads));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
@@ -933,6 +942,7 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   if (L.alt) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 3>, L, maps_dev));
   else if (L.epi8 >= 4) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads16, 1>, L, maps_dev));
   else if (L.epi8 && L.fold) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 2>, L, maps_dev));
+  else if (L.epi8 && add) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 1, true>, L, maps_dev));
   else if (L.epi8) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 1>, L, maps_dev));
   else PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads, 0>, L, maps_dev));
   return 0;
