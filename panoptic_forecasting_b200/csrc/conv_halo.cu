@@ -278,7 +278,10 @@ __device__ __forceinline__ void mma_warp_loop(const HaloLayer& L, const MmaCtx& 
 // owns accumulator buffer k, so the epilogue of tile i + 1 runs next to that of tile i instead of behind it
 // ADD: the epilogue carries the additive term of the fused conv1x1_up layers (only <352, 1> is instantiated with it: its
 // eight source addresses and interpolation weights otherwise sit in the registers of every wide layer)
-template <int THREADS, int MODE, bool ADD = false>
+// LEAN: the epilogue of the common ConvLayer (ReLU, split-bf16 output at the layer's own resolution: no pooling, no
+// space-to-depth, no fp32 / argmax output) -- those run-time switches were a dozen uniform branches per 16-channel group,
+// and the epilogue warps lost 12-16 % of their issue slots to instruction fetch on them (ncu source view, stall_no_inst)
+template <int THREADS, int MODE, bool ADD = false, bool LEAN = false>
 __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L, const CUtensorMap* __restrict__ maps) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxB + 9];
@@ -538,11 +541,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
       if (dbg && tc_ == 0 && threadIdx.x == 64) L.dbg_ts[5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // pool: the even/even pixel of each 2x2 block stores the average, into the half-resolution tensor
-      const bool store_px = L.pool ? (!ghost && ((m & 9) == 0) && (oy >> 1) < (L.Hout >> 1) && (ox >> 1) < (L.Wout >> 1)) : inside;
-      const size_t pix = L.s2d_block
+      const bool pool = !LEAN && L.pool;
+      const int s2d_block = LEAN ? 0 : L.s2d_block;
+      const bool store_px = pool ? (!ghost && ((m & 9) == 0) && (oy >> 1) < (L.Hout >> 1) && (ox >> 1) < (L.Wout >> 1)) : inside;
+      const size_t pix = s2d_block
                              ? (size_t)img * L.out_img_stride + ((size_t)(oy >> 1) * (L.Wout >> 1) + (ox >> 1)) * L.out_cs +
-                                   (size_t)((oy & 1) * 2 + (ox & 1)) * L.s2d_block
-                             : L.pool ? (size_t)img * L.out_img_stride + ((size_t)(oy >> 1) * (L.Wout >> 1) + (ox >> 1)) * L.out_cs
+                                   (size_t)((oy & 1) * 2 + (ox & 1)) * s2d_block
+                             : pool ? (size_t)img * L.out_img_stride + ((size_t)(oy >> 1) * (L.Wout >> 1) + (ox >> 1)) * L.out_cs
                                       : (size_t)img * L.out_img_stride + ((size_t)oy * L.Wout + ox) * L.out_cs;
       // bilinear source of the optional additive term (conv1x1_up fused with TransitionUp)
       const float *a00 = nullptr, *a01 = nullptr, *a10 = nullptr, *a11 = nullptr;
@@ -603,11 +608,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
             v[4 * i + 3] += ahy * (ahx * p.w + alx * q4.w) + aly * (ahx * r4.w + alx * s4.w);
           }
         }
-        if (L.relu) {
+        if (LEAN || L.relu) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (L.pool) {
+        if (pool) {
           // AvgPool2d(2,2) of the ReLU'd outputs: lane bits 0 / 3 are the column / row parity inside the 16 x 8 tile
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
           }
         }
         if (!store_px || (kHaloDbg && (L.dbg_mode & 2))) return;
-        if (L.out_f32) {
+        if (!LEAN && L.out_f32) {
           if (L.amax_ncls > 0 && n == 0) {
             // first maximum of the class logits (torch.argmax tie rule), parked in the padding channel for the
             // fused upsample + argmax kernel: a full-resolution pixel whose source pixels agree needs no interpolation
@@ -899,12 +904,13 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
     PF_CHECK_CUDA(cudaGetDevice(&dev));
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      PF_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kHaloThreads8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      const void* fns[] = {(const void*)conv_halo_kernel<kHaloThreads, 0>, (const void*)conv_halo_kernel<kHaloThreads, 0, false, true>,
+                           (const void*)conv_halo_kernel<kHaloThreads8, 2>,
+                           (const void*)conv_halo_kernel<kHaloThreads8, 1>, (const void*)conv_halo_kernel<kHaloThreads8, 1, false, true>,
+                           (const void*)conv_halo_kernel<kHaloThreads8, 1, true, true>,
+                           (const void*)conv_halo_kernel<kHaloThreads16, 1>, (const void*)conv_halo_kernel<kHaloThreads16, 1, false, true>,
+                           (const void*)conv_halo_kernel<kHaloThreads8, 3>, (const void*)conv_halo_kernel<kHaloThreads8, 3, false, true>};
+      for (const void* f : fns) PF_CHECK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
       attr_done.fetch_or(bit, std::memory_order_release);
     }
   }
@@ -939,12 +945,18 @@ int launch_conv_halo(const HaloLayer& L, const CUtensorMap* maps_dev, int nblock
   }
   cfg.attrs = attr_pdl;
   cfg.numAttrs = na;
-  if (L.alt) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 3>, L, maps_dev));
-  else if (L.epi8 >= 4) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads16, 1>, L, maps_dev));
-  else if (L.epi8 && L.fold) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 2>, L, maps_dev));
-  else if (L.epi8 && add) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 1, true>, L, maps_dev));
-  else if (L.epi8) PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads8, 1>, L, maps_dev));
-  else PF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<kHaloThreads, 0>, L, maps_dev));
+  // the common epilogue (see LEAN); the additive-term layers (ReLU, plain split-bf16 output) always have it
+  const bool lean = L.relu && !L.pool && !L.s2d_block && !L.out_f32 && !L.amax_ncls;
+  PF_REQUIRE(!add || lean, PF_ESTATE, "halo kernel: the additive-term layers are plain ReLU ConvLayers");
+  const void* fn;
+  if (L.alt) fn = lean ? (const void*)conv_halo_kernel<kHaloThreads8, 3, false, true> : (const void*)conv_halo_kernel<kHaloThreads8, 3>;
+  else if (L.epi8 >= 4) fn = lean ? (const void*)conv_halo_kernel<kHaloThreads16, 1, false, true> : (const void*)conv_halo_kernel<kHaloThreads16, 1>;
+  else if (L.epi8 && L.fold) fn = (const void*)conv_halo_kernel<kHaloThreads8, 2>;
+  else if (L.epi8 && add) fn = (const void*)conv_halo_kernel<kHaloThreads8, 1, true, true>;
+  else if (L.epi8) fn = lean ? (const void*)conv_halo_kernel<kHaloThreads8, 1, false, true> : (const void*)conv_halo_kernel<kHaloThreads8, 1>;
+  else fn = lean ? (const void*)conv_halo_kernel<kHaloThreads, 0, false, true> : (const void*)conv_halo_kernel<kHaloThreads, 0>;
+  void* args[] = {(void*)&L, (void*)&maps_dev};
+  PF_CHECK_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   return 0;
 }
 
