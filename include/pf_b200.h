@@ -152,6 +152,8 @@ int pf_bgnet_load_conv(pf_bgnet_t* net, int i, const float* weight, const float*
 int pf_bgnet_load_final(pf_bgnet_t* net, const float* weight /*[classes,48]*/, const float* bias);
 int pf_bgnet_set_depth_norm(pf_bgnet_t* net, float mean, float std);
 
+/* 0 for an unsupported size: H must be a multiple of 4, W a multiple of 16, both >= 64 (the two stride-2 convs halve
+ * exactly, the four AvgPool2d(2,2) floor like the reference's, hardnet.py:300). */
 size_t pf_bgnet_workspace_bytes(const pf_bgnet_t* net, int b, int H, int W);
 
 /*   labels_dev  u8  [b,t,H,W]   class ids; ids >= num_classes contribute an all-zero one-hot
