@@ -162,13 +162,14 @@ def hop_np(d, mn=0.1, mx=200.0):
 
 @pytest.mark.parametrize("dist", ["R", "U"])
 @pytest.mark.parametrize("shape", [(2, 3, 64, 128), (2, 3, 40, 96), (2, 3, 30, 72), (1, 3, 256, 512)])
-@pytest.mark.parametrize("fast", ["0", "1"])
-def test_packed_inputs_bit_exact(pf_lib, bg_shapes, monkeypatch, dist, shape, fast):
+@pytest.mark.parametrize("fast,pipe", [("0", "1"), ("0", "0"), ("1", "1")], ids=["generic-pipelined", "generic-plain", "fast"])
+def test_packed_inputs_bit_exact(pf_lib, bg_shapes, monkeypatch, dist, shape, fast, pipe):
     """pf_zsplat_forward_frames_hop_packed (uint16 depth code + table, 1-bit mask) == the reference-format entry
     point on depth = lut[code] == oracle + disk hop, bit for bit (fast kernel for W % 128 == 0, generic otherwise)."""
     from conftest import bg_params
     from panoptic_forecasting_b200.pipeline import BGForecastPipeline
     monkeypatch.setenv("PF_ZSPLAT_FAST", fast)
+    monkeypatch.setenv("PF_ZSPLAT_PIPE", pipe)       # pipelined code / table loads of the generic point kernel (default on)
     b, t, h, w = shape
     packed, unpacked = synthetic.pack_pc_inputs(synthetic.make_pc_inputs(b=b, t=t, h=h, w=w, dist=dist, seed=3 + w))
     npin = with_inverses(unpacked)
