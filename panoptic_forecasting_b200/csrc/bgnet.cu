@@ -1298,12 +1298,22 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
       !L->resident) {
     // 48 couts whose weights have to be streamed per tile: three folded CTAs of 16 couts with resident weights instead
     // (108->46 at 1/8: 114 -> 102 us)
+    // (second half of round 2) two CTAs of 24 couts: MMA N = 144 / 80, the activation boxes fetched twice instead of
+    // three times.  PF_HALO_FOLD_48: 0 = unfolded, 3 = the three-way split.
     const char* f48 = getenv("PF_HALO_FOLD_48");
     if (!(f48 && f48[0] == '0')) {
       HaloLayer T = *L;
       size_t sm2 = 0;
-      T.ntile = 16;
-      if (plan_fold(&T, &sm2) && T.stages_a >= 3) { *L = T; *smem = sm2; ntile = 16; nb = 3; }
+      bool done = false;
+      if (!(f48 && f48[0] == '3')) {
+        T.ntile = 24;
+        if (plan_fold(&T, &sm2) && T.stages_a >= 3) { *L = T; *smem = sm2; ntile = 24; nb = 2; done = true; }
+      }
+      if (!done) {
+        T = *L; sm2 = 0;
+        T.ntile = 16;
+        if (plan_fold(&T, &sm2) && T.stages_a >= 3) { *L = T; *smem = sm2; ntile = 16; nb = 3; }
+      }
     }
   }
   used[0] = used[1] = used[2] = false;

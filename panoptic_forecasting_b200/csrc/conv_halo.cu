@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bias_r[g][i] = (ntile <= 32 && g * 16 < ntile && n0 + g * 16 < L.cout_store) ? __ldg(L.bias + n0 + g * 16 + i) : 0.f;
+      for (int i = 0; i < 16; ++i) bias_r[g][i] = (ntile <= 32 && g * 16 < ntile && n0 + g * 16 + i < L.cout_store) ? __ldg(L.bias + n0 + g * 16 + i) : 0.f;
     // wide path (ntile > 32): the bias of this warp's first two 16-channel groups (all it has when ntile <= 64 with two
     // teams, or <= 32 with one)
     float bias_w[2][16];
@@ -581,7 +581,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty(acc));
       };
-      auto finish16 = [&](float (&v)[16], const int n) {     // v = conv + bias of channels [n, n + 16)
+      // nv = 16, or 8 when only the first eight channels are this CTA's to write (N tile of 24 next to another block)
+      auto finish16 = [&](float (&v)[16], const int n, const int nv = 16) {     // v = conv + bias of channels [n, n + 16)
         if (ADD && s00) {
           // four products per channel (the weights are per pixel): the interpolation costs 4 FMAs instead of 3 lerps
           const float w00 = (1.f - aly) * (1.f - alx), w01 = (1.f - aly) * alx, w10 = aly * (1.f - alx), w11 = aly * alx;
@@ -648,8 +649,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
         }
         // one 256-bit store per plane: the pixel's 16 channels are one 32-byte sector (two 128-bit stores wrote each
         // sector in halves)
-        st_global_256(L.out_hi + pix + n, h[0], h[1]);
-        st_global_256(L.out_lo + pix + n, l[0], l[1]);
+        if (nv == 16 && (n & 15) == 0) {
+          st_global_256(L.out_hi + pix + n, h[0], h[1]);
+          st_global_256(L.out_lo + pix + n, l[0], l[1]);
+        } else {
+          // second block of a 2 x 24 split (channel offset 24: 16-byte aligned only) or a half group
+          *reinterpret_cast<uint4*>(L.out_hi + pix + n) = h[0];
+          *reinterpret_cast<uint4*>(L.out_lo + pix + n) = l[0];
+          if (nv == 16) {
+            *reinterpret_cast<uint4*>(L.out_hi + pix + n + 8) = h[1];
+            *reinterpret_cast<uint4*>(L.out_lo + pix + n + 8) = l[1];
+          }
+        }
       };
       if (MODE != 1 && L.fold) {
         // six 16-column pieces per 16 output channels: (hi, lo) parts of the dx = 0, 1, 2 blocks.  Output column x takes
@@ -683,7 +694,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
             // n = 24: columns 24..31 of a block are the next block's -- the slot's padding channels are written as zeros
             if (g * 16 + i >= ntile) v[i] = 0.f;
           }
-          finish16(v, n0 + g * 16);
+          // channels this CTA may write: its own N tile, up to the slot's padded end when it is the last block
+          const int lim = (n0 + ntile < L.cout_store) ? n0 + ntile : L.cout_store;
+          finish16(v, n0 + g * 16, lim - (n0 + g * 16) >= 16 ? 16 : 8);
         }
       } else if ((MODE == 0 || MODE == 3) && ntile <= 32) {
         // whole accumulator row in registers (2 or 4 loads in flight), buffer released, then the math and the stores
