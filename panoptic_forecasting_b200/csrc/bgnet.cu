@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(256) upsample_argmax_strip_kernel(const float*
   }
   float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   int arg[4] = {0, 0, 0, 0};
-  bool a1[4], b1[4], b2[4];
+  float wc[4][3];                                             // weights of the three source columns for each of the 4 pixels
   float lx[4], hx[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -855,7 +855,11 @@ __global__ void __launch_bounds__(256) upsample_argmax_strip_kernel(const float*
     lx[j] = fx - (float)x0; hx[j] = 1.f - lx[j];
     const int ia = x0 - c0;                                   // 0 or 1: left column of pixel j within {cA, cB, cC}
     const int ib = ia + (x0 < w - 1 ? 1 : 0);                 // 0..2: right column
-    a1[j] = ia != 0; b1[j] = ib == 1; b2[j] = ib == 2;
+    // one of the three weights is zero: a 3-term weighted sum (FMUL + 2 FFMA per class) instead of two column selects
+    // per class and pixel (a fifth of the kernel's instructions); 0 * column adds exactly nothing
+    wc[j][0] = (ia == 0 ? hx[j] : 0.f) + (ib == 0 ? lx[j] : 0.f);
+    wc[j][1] = (ia == 1 ? hx[j] : 0.f) + (ib == 1 ? lx[j] : 0.f);
+    wc[j][2] = ib == 2 ? lx[j] : 0.f;
   }
   const int nq = (ncls + 3) >> 2;
 #pragma unroll
@@ -872,13 +876,11 @@ __global__ void __launch_bounds__(256) upsample_argmax_strip_kernel(const float*
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       // vertical interpolation once per source column (shared by the strip's pixels), then the horizontal blend
-      const float4 a = a1[j] ? col[1] : col[0];
-      const float4 b_ = b2[j] ? col[2] : (b1[j] ? col[1] : col[0]);
       float v[4];
-      v[0] = hx[j] * a.x + lx[j] * b_.x;
-      v[1] = hx[j] * a.y + lx[j] * b_.y;
-      v[2] = hx[j] * a.z + lx[j] * b_.z;
-      v[3] = hx[j] * a.w + lx[j] * b_.w;
+      v[0] = fmaf(wc[j][2], col[2].x, fmaf(wc[j][1], col[1].x, wc[j][0] * col[0].x));
+      v[1] = fmaf(wc[j][2], col[2].y, fmaf(wc[j][1], col[1].y, wc[j][0] * col[0].y));
+      v[2] = fmaf(wc[j][2], col[2].z, fmaf(wc[j][1], col[1].z, wc[j][0] * col[0].z));
+      v[3] = fmaf(wc[j][2], col[2].w, fmaf(wc[j][1], col[1].w, wc[j][0] * col[0].w));
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = k * 4 + e;
