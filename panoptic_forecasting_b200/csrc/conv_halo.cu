@@ -694,8 +694,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const HaloLayer L
             // n = 24: columns 24..31 of a block are the next block's -- the slot's padding channels are written as zeros
             if (g * 16 + i >= ntile) v[i] = 0.f;
           }
-          // channels this CTA may write: its own N tile, up to the slot's padded end when it is the last block
-          const int lim = (n0 + ntile < L.cout_store) ? n0 + ntile : L.cout_store;
+          // channels this CTA may write: its own N tile, and up to the slot's padded end when it is the LAST N block (a
+          // single block of 24 couts writes the slot's channels 24..31 as zeros: nobody else does, and stale NaN
+          // patterns there would turn into zeros behind the consumers' ReLU -- silently wrong)
+          const int lim = (blockIdx.y + 1 < gridDim.y) ? n0 + ntile : L.cout_store;
           finish16(v, n0 + g * 16, lim - (n0 + g * 16) >= 16 ? 16 : 8);
         }
       } else if ((MODE == 0 || MODE == 3) && ntile <= 32) {

@@ -156,3 +156,24 @@ def test_label_only_fast_path_matches_interpolated_argmax(pf_lib, bg_shapes, mon
     assert torch.equal(slow.long(), full["seg"].long())
     n_diff = int((fast.long() != full["seg"].long()).sum())
     assert n_diff <= 1e-5 * fast.numel(), n_diff
+
+
+@pytest.mark.parametrize("precision,tol", [("tc", 3e-4), ("fp32", 1e-4)])
+def test_poisoned_workspace(pf_lib, bg_shapes, precision, tol):
+    """Every byte of the activation arena that a kernel reads must have been written by the same forward: the work space
+    is filled with 0xFF (NaN patterns in bf16 and fp32) between two calls.  A NaN accumulator becomes 0 behind ReLU
+    (fmaxf), so an uninitialised padding channel is a silently wrong result, not a NaN -- hence the comparison with the
+    oracle, at a size where the layers keep their full N tiles (N = 24 single blocks, 2 x 24 splits, pooled epilogues)."""
+    b, h, w = 2, 256, 512
+    sd = synthetic.make_bg_state_dict(bg_shapes, seed=21)
+    pc = synthetic.make_pc_inputs(b, 3, h, w, "R", seed=21)
+    inp = {"seg": pc["seg"].long(), "depth": pc["depth"].clamp(0.1, 200), "depth_mask": pc["depth_mask"]}
+    ref = bg_oracle.predict(sd, inp, None)
+    m = gpu_model(sd, None, precision=precision)
+    cu = {k: v.cuda() for k, v in inp.items()}
+    first = m.predict(cu, {})
+    m._ws.fill_(0xFF)
+    out = m.predict(cu, {})
+    assert torch.isfinite(out["logits"]).all()
+    check_against(out, ref, rel_tol=tol)
+    assert torch.equal(out["logits"], first["logits"]) or (out["logits"] - first["logits"]).abs().max().item() <= tol * ref["logits"].abs().max().item()
