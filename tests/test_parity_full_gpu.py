@@ -95,7 +95,11 @@ def test_benched_config_parity(pf_lib, bg_shapes, dist, packed):
     # ---- batch 16 (bench.py's batch): 8 copies of the two items.  The conv plan (N split, folded form) depends on
     # the tile count, so the fp32 summation order may differ from batch 2: every copy must still meet the same bar.
     rep = {k: (v.repeat(8, *([1] * (v.dim() - 1))) if v.dim() > 1 and v.shape[0] == b else v) for k, v in cu.items()}
-    out16 = BGForecastPipeline(model(return_logits=False, seg_dtype="uint8")).forecast(rep)
+    pipe16 = BGForecastPipeline(model(return_logits=False, seg_dtype="uint8"))
+    pipe16.forecast(rep)                       # allocates both work spaces ...
+    pipe16.bg._ws.fill_(0xFF)                  # ... which are then poisoned (NaN patterns / all-ones keys): every byte a
+    pipe16._ws.fill_(0xFF)                     # kernel reads has to be written by the same call (see test_poisoned_workspace)
+    out16 = pipe16.forecast(rep)
     assert out16["seg"].shape[0] == 16
     assert torch.equal(out16["warped_seg"][:2].cpu().long(), bg_in["seg"]) and torch.equal(out16["warped_seg"][14:].cpu().long(), bg_in["seg"])
     n16 = 0
