@@ -1378,12 +1378,12 @@ static int build_halo_layer(pf_bgnet* net, int i, const TcIo& io, std::vector<CU
     L->epi8 = (!L->fold && e8min > 0 && L->ntile >= e8min && L->ntile >= 32) ? 2 : 0;       // epilogue teams (0 = one)
     // four teams (608 threads, one group per round) for N tiles >= 64: base.5 216 -> 185 us, base.8 98 -> 74 us per 16
     // frames; not for the fused conv1x1_up layers, whose interpolating epilogue got slower (365 -> 381 us).
-    // A/B PF_HALO_EPI16: 0 = never, 1 = also for those.
+    // A/B PF_HALO_EPI16=0: never.
     const char* ft = getenv("PF_HALO_FOLD_TEAMS");         // A/B: two epilogue teams for folded layers with two 16-channel groups
     if (L->fold && L->ntile == 32 && ft && ft[0] == '1') L->epi8 = 2;
     const char* e16 = getenv("PF_HALO_EPI16");
-    const bool never = e16 && e16[0] == '0', always = e16 && e16[0] == '1';
-    (void)always;                                          // (the four-team kernel no longer carries the additive term)
+    const bool never = e16 && e16[0] == '0';               // (the four-team kernel carries no additive term: never for
+                                                           // the fused conv1x1_up layers, whatever the switch says)
     if (L->epi8 && L->ntile >= 64 && !never && !L->add_pbytes && !add_patch) L->epi8 = 4;
     // alternate-tile epilogue teams (conv_halo_kernel<352, 3>: team k owns accumulator buffer k) for N tiles <= 32.
     // Measured per 16 frames: base.1 (16->24 at 1/2 resolution, one 16-channel chunk = 18 MMAs per tile, the epilogue

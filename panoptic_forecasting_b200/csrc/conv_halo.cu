@@ -14,10 +14,18 @@
 // high-resolution layers, where a CTA visits many tiles) or STREAMED per (chunk, tap) through a
 // second mbarrier ring.  The fp32 accumulator is double-buffered in TMEM so the epilogue of tile
 // i overlaps the MMAs of tile i+1.
-// Warp roles (352 threads): warp 0 TMA producer, warps 1 and 6 MMA issuers (alternate chunks; warp 1 owns TMEM),
-// warps 2..5 epilogue; for layers with >= 64 output channels per CTA (the 1x1 transition / conv1x1_up layers, which are
-// bound by the epilogue: TMEM reads, bias / ReLU / pool / interpolation, split, stores) warps 7..10 are a second
-// epilogue team that takes every other 16-channel group of the same accumulator rows (HaloLayer::epi8).
+// Warp roles: warp 0 TMA producer, warps 1 and 6 MMA issuers (alternate chunks; warp 1 owns TMEM), warps 2..5 the
+// epilogue team (TMEM reads, bias / ReLU / pool / interpolation, split, stores).  Instantiations
+// conv_halo_kernel<threads, mode, add, lean>:
+//   224 threads, mode 0   one epilogue team, every epilogue path (folded / whole row in registers / wide)
+//   352 threads, mode 1   a second team (warps 7..10) takes every other 16-channel group of the same accumulator rows
+//                         (N tiles >= 32: the 1x1 transition / conv1x1_up layers, base.2, base.3)
+//   352 threads, mode 3   two teams on ALTERNATE TILES, team k owns accumulator buffer k (base.1 and the single-chunk
+//                         folded layers: a tile is a dozen MMAs, the epilogue is the whole cost)
+//   608 threads, mode 1   four teams for N tiles >= 64 (no additive term: 86 registers)
+//   352 threads, mode 2   A/B only: two teams on the two groups of a folded N = 32 layer
+//   add   = the additive term of the fused conv1x1_up layers (only <352, 1, true, true>)
+//   lean  = the common ConvLayer epilogue: ReLU + split-bf16 store, none of the pool / space-to-depth / fp32 switches
 #include <atomic>
 
 #include <cuda.h>
@@ -42,7 +50,7 @@ constexpr bool kHaloDbg = true;
 constexpr bool kHaloDbg = false;
 #endif
 constexpr int kMaxA = 8, kMaxB = 8;
-constexpr int kHaloThreads = 224, kHaloThreads8 = 352, kHaloThreads16 = 608;   // 1 / 2 / 4 epilogue teams      // warp 0 TMA producer, warps 1 and 6 MMA issuers, warps 2..5 (+ 7..10: HaloLayer::epi8) epilogue
+constexpr int kHaloThreads = 224, kHaloThreads8 = 352, kHaloThreads16 = 608;   // 1 / 2 / 4 epilogue teams
 
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
