@@ -64,6 +64,25 @@ def test_cpu_tensors_fail_loudly(pf_lib):
         pc.predict(synthetic.make_pc_inputs(1, 3, 8, 8), {})
 
 
+def test_dense_mode_and_loss_host_logic(pf_lib):
+    """`convert2onehot: False` builds the same parameter tree; CPU tensors, .train() and a label tensor in dense mode are
+    refused before any CUDA call (no CPU fallback, no silent reinterpretation)."""
+    p = bg_params()
+    p["model"] = dict(p["model"], convert2onehot=False)
+    md = build_model(p).eval()
+    assert set(md.state_dict()) == set(build_model(bg_params()).state_dict())
+    x = synthetic.make_bg_dense_inputs(1, 3, 64, 64)
+    assert x["seg"].shape == (1, 3, 11, 64, 64) and abs(x["seg"].sum(2) - 1).max() < 1e-5
+    with pytest.raises(_lib.PFError):
+        md.predict(x, {})
+    target = synthetic.make_loss_target(x["seg"].argmax(2)[:, 0])
+    assert (target[:, :5] == 255).all() and target.dtype.is_floating_point is False
+    with pytest.raises(_lib.PFError):
+        md.loss(x, {"seg": target})
+    with pytest.raises(NotImplementedError):
+        md.train().loss(x, {"seg": target})
+
+
 def test_synthetic_inputs_are_seeded_and_shaped():
     a = synthetic.make_pc_inputs(b=2, t=3, h=32, w=64, dist="R", seed=7)
     b = synthetic.make_pc_inputs(b=2, t=3, h=32, w=64, dist="R", seed=7)
